@@ -1,0 +1,77 @@
+// Library plumbing: error slot, launch counter, init, memory, copies.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "adb_internal.h"
+
+namespace adb {
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace adb
+
+extern "C" {
+
+const char* adb_last_error(void) { return adb::g_err; }
+const char* adb_version(void) { return "adb200 0.1 (sm_100a)"; }
+int64_t adb_launch_count(void) { return adb::g_launches.load(); }
+
+int adb_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return adb::set_error("adb_init: no CUDA device visible (%s) — this backend has no CPU path",
+                              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    ADB_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp p;
+    ADB_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return adb::set_error("adb_init: device %s is sm_%d%d; this library is built for sm_100a only", p.name, p.major, p.minor);
+    return 0;
+}
+
+int adb_sync(void* stream) {
+    ADB_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int adb_malloc(void** out, size_t bytes, void* stream) {
+    ADB_CUDA_OK(cudaMallocAsync(out, bytes ? bytes : 16, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_free(void* ptr, void* stream) {
+    if (!ptr) return 0;
+    ADB_CUDA_OK(cudaFreeAsync(ptr, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream) {
+    if (!bytes) return 0;
+    ADB_CUDA_OK(cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream) {
+    if (!bytes) return 0;
+    ADB_CUDA_OK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_host_alloc(void** out, size_t bytes) {
+    ADB_CUDA_OK(cudaMallocHost(out, bytes ? bytes : 16));
+    return 0;
+}
+int adb_host_free(void* ptr) {
+    if (!ptr) return 0;
+    ADB_CUDA_OK(cudaFreeHost(ptr));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,452 @@
+// FP64 strided-batched GEMM for sm_100a — the contraction kernel behind Einsum.forward
+// (replaces np.einsum at reference autodiff/core/ops.py:180 for true contractions).
+//
+//   C[b][m][n] = sum_k A[b][m][k] * B[b][k][n]        (all strides in elements, any of NN/NT/TN/TT)
+//
+// Fast path (gemm_tma_kernel): TMA (cp.async.bulk.tensor, 128B swizzle) -> 6-stage shared-memory ring
+// guarded by mbarriers -> 8 warps issuing DMMA.8x8x4 (mma.sync.m8n8k4.f64) on 64x32 warp tiles ->
+// direct register epilogue.  Lane 0 of warp 0 doubles as the TMA producer (4 k-tiles ahead).  tcgen05 has no f64 kind
+// (ptxas rejects .kind::f64), so on B200 the FP64 tensor path IS the warp-level DMMA; measured issue
+// peak 37.0 TFLOP/s (profiles/r01_probe_fp64_issue_rates.log).
+//
+// Shared-memory fragment addressing is conflict-free under the TMA 128B swizzle for both operand
+// layouts (see DESIGN.md "GEMM fragment maps"):
+//   K-contiguous operand ("KC"): tile = [128 rows][16 k] (one TMA box), one LDS.128 yields the k-pair
+//        (8h+2q, 8h+2q+1) used by two consecutive k4-steps; MMA row g <-> tile row (g>>1)|((g&1)<<2).
+//   MN-contiguous operand ("MC"): tile = 8 blocks of [16 k][16 mn] (eight TMA boxes), one LDS.128 yields
+//        two interleaved 8-wide MMA tiles (columns 2g and 2g+1) for one k4-step.
+//   Both use the k-slot map  q -> k = 8h + 2q + p  so A and B fragments always agree.
+//
+// Fallback (gemm_generic_kernel): any stride / any alignment, 64x64 DFMA register tiling.  Used only
+// when an operand cannot be described by a TMA tensor map (unaligned base or pitch).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "adb_internal.h"
+
+namespace adb {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 6;
+constexpr int A_TILE_BYTES = BM * BK * 8;   // 16 KiB
+constexpr int B_TILE_BYTES = BN * BK * 8;   // 16 KiB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = CONSUMER_WARPS * 32;   // 9 warps would round to 12 for register allocation (168 regs)
+constexpr int PREFETCH = STAGES - 2;                   // the slot refilled at step kt was released at kt-2: no stall
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 lds128(const unsigned char* p) { return *reinterpret_cast<const double2*>(p); }
+
+struct GemmParams {
+    int M, N, K;
+    int tiles_m, tiles_n;
+    double* C;
+    long long c_sm, c_sn, c_sb;
+};
+
+// ----------------------------------------------------------------------------- TMA + DMMA kernel
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // keep the pointer derived from the __shared__ array so loads compile to LDS (not generic LD)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = smem_u32(bars + STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // grouped rasterisation: 8 tile-rows share their B column panels in L2
+    const int GROUP = 8;
+    const int tile = blockIdx.x;
+    const int group_size = GROUP * p.tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(p.tiles_m - first_m, GROUP);
+    const int tm = first_m + (tile % group_size) % gm;
+    const int tn = (tile % group_size) / gm;
+    const int m0 = tm * BM, n0 = tn * BN;
+    const int batch = blockIdx.y;
+    const int num_kt = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ===== TMA producer: lane 0 of warp 0 keeps PREFETCH k-tiles in flight (issued between its own MMAs) =====
+    auto issue_tile = [&](int kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t fb = full0 + 8 * s;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_TILE_BYTES;
+        const int k0 = kt * BK;
+        if (A_KC) {
+            tma_load_3d(sa, &tmA, fb, k0, m0, batch);
+        } else {
+#pragma unroll
+            for (int b = 0; b < BM / 16; ++b) tma_load_3d(sa + b * 2048, &tmA, fb, m0 + 16 * b, k0, batch);
+        }
+        if (B_KC) {
+            tma_load_3d(sb, &tmB, fb, k0, n0, batch);
+        } else {
+#pragma unroll
+            for (int b = 0; b < BN / 16; ++b) tma_load_3d(sb + b * 2048, &tmB, fb, n0 + 16 * b, k0, batch);
+        }
+    };
+    const bool is_producer = threadIdx.x == 0;
+    if (is_producer) {
+        const int npre = num_kt < PREFETCH ? num_kt : PREFETCH;
+        for (int kt = 0; kt < npre; ++kt) issue_tile(kt);
+    }
+
+    // ===== consumers: 2 (M) x 4 (N) warps, warp tile 64 x 32 =====
+    const int warp_m = warp & 1;
+    const int warp_n = warp >> 1;
+    const int g = lane >> 2;
+    const int q = lane & 3;
+    const int rmap = (g >> 1) | ((g & 1) << 2);
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // per-thread byte offsets inside a stage
+    const int a_off = A_KC ? (warp_m * 64 + rmap) * 128 : warp_m * 4 * 2048;
+    const int b_off = A_TILE_BYTES + (B_KC ? (warp_n * 32 + rmap) * 128 : warp_n * 2 * 2048);
+
+    for (int kt = 0; kt < num_kt; ++kt) {
+        if (is_producer && kt + PREFETCH < num_kt) issue_tile(kt + PREFETCH);
+        __syncwarp();
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        const unsigned char* st = smem + s * STAGE_BYTES;
+        const unsigned char* sA = st + a_off;
+        const unsigned char* sB = st + b_off;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double a[2][8], b[2][4];
+            if (A_KC) {
+                const int ch = ((4 * h + q) ^ rmap) << 4;
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt) {
+                    const double2 v = lds128(sA + mt * 1024 + ch);
+                    a[0][mt] = v.x;
+                    a[1][mt] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int kr = 8 * h + 2 * q + pp;
+                    const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
+#pragma unroll
+                    for (int blk = 0; blk < 4; ++blk) {
+                        const double2 v = lds128(sA + blk * 2048 + off);
+                        a[pp][2 * blk] = v.x;
+                        a[pp][2 * blk + 1] = v.y;
+                    }
+                }
+            }
+            if (B_KC) {
+                const int ch = ((4 * h + q) ^ rmap) << 4;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const double2 v = lds128(sB + nt * 1024 + ch);
+                    b[0][nt] = v.x;
+                    b[1][nt] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int kr = 8 * h + 2 * q + pp;
+                    const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const double2 v = lds128(sB + blk * 2048 + off);
+                        b[pp][2 * blk] = v.x;
+                        b[pp][2 * blk + 1] = v.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    }
+
+    // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
+    double* __restrict__ Cb = p.C + (long long)batch * p.c_sb;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+        const int row = m0 + warp_m * 64 + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
+        if (row >= p.M) continue;
+        double* crow = Cb + (long long)row * p.c_sm;
+        if (B_KC) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = n0 + warp_n * 32 + nt * 8 + q + 4 * e;
+                    if (col < p.N) crow[(long long)col * p.c_sn] = acc[mt][nt][e];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                // thread owns 4 consecutive columns: 4q + {0,1,2,3} = (e=0,j=0),(e=0,j=1),(e=1,j=0),(e=1,j=1)
+                const int col = n0 + warp_n * 32 + blk * 16 + 4 * q;
+                const double v0 = acc[mt][2 * blk][0], v1 = acc[mt][2 * blk + 1][0];
+                const double v2 = acc[mt][2 * blk][1], v3 = acc[mt][2 * blk + 1][1];
+                double* cp = crow + (long long)col * p.c_sn;
+                if (p.c_sn == 1 && col + 3 < p.N && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+                    reinterpret_cast<double2*>(cp)[0] = make_double2(v0, v1);
+                    reinterpret_cast<double2*>(cp)[1] = make_double2(v2, v3);
+                } else {
+                    if (col < p.N) cp[0] = v0;
+                    if (col + 1 < p.N) cp[p.c_sn] = v1;
+                    if (col + 2 < p.N) cp[2 * p.c_sn] = v2;
+                    if (col + 3 < p.N) cp[3 * p.c_sn] = v3;
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- generic fallback
+// 64x64 tile, 256 threads, 4x4 per thread, BK=16; arbitrary element strides.
+__global__ void __launch_bounds__(256)
+gemm_generic_kernel(int M, int N, int K,
+                    const double* __restrict__ A, long long a_sm, long long a_sk, long long a_sb,
+                    const double* __restrict__ B, long long b_sk, long long b_sn, long long b_sb,
+                    double* __restrict__ C, long long c_sm, long long c_sn, long long c_sb) {
+    __shared__ double As[16][64 + 1];
+    __shared__ double Bs[16][64 + 1];
+    const int batch = blockIdx.z;
+    A += (long long)batch * a_sb;
+    B += (long long)batch * b_sb;
+    C += (long long)batch * c_sb;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            // choose the faster-varying index to follow the contiguous direction where possible
+            int mm, kk;
+            if (a_sk == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
+            const int gmm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gmm < M && gk < K) ? A[(long long)gmm * a_sm + (long long)gk * a_sk] : 0.0;
+            int nn, kb;
+            if (b_sk == 1) { kb = i & 15; nn = i >> 4; } else { nn = i & 63; kb = i >> 6; }
+            const int gn = n0 + nn, gkb = k0 + kb;
+            Bs[kb][nn] = (gn < N && gkb < K) ? B[(long long)gkb * b_sk + (long long)gn * b_sn] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + ty + 16 * i;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx + 16 * j;
+            if (col < N) C[(long long)row * c_sm + (long long)col * c_sn] = acc[i][j];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static bool load_encode() {
+    if (g_encode) return true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return true;
+}
+
+// One operand of a batched 2-D problem, as TMA sees it: `inner` is the stride-1 extent.
+static bool make_tmap(CUtensorMap* map, const double* base, long long inner, long long outer, long long batch,
+                      long long outer_stride, long long batch_stride, int box_inner, int box_outer) {
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)outer_stride * 8ull, (cuuint64_t)batch_stride * 8ull};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static bool tma_ok(const double* base, long long s_other, long long s_batch, long long batch) {
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+    if (s_other <= 0 || (s_other & 1)) return false;
+    if (batch > 1 && (s_batch <= 0 || (s_batch & 1))) return false;
+    return true;
+}
+
+template <bool A_KC, bool B_KC>
+static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = gemm_tma_kernel<A_KC, B_KC>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, 1);
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("gemm_tma launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
+    const long long M = d->M, N = d->N, K = d->K, batch = d->batch;
+    if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return set_error("gemm: extent too large");
+    if (K <= 0) return set_error("gemm: K must be positive (caller zero-fills)");
+
+    // strides of size-1 dims are meaningless; normalise them so layout detection and TMA encoding are clean
+    adb_gemm_desc dd = *d;
+    if (K == 1) { dd.a_sk = 1; dd.b_sk = 1; if (dd.a_sm == 1 && M > 1) dd.a_sk = 0; if (dd.b_sn == 1 && N > 1) dd.b_sk = 0; }
+    if (M == 1 && dd.a_sk == 1) dd.a_sm = (K + 1) & ~1LL;
+    if (N == 1 && dd.b_sk == 1) dd.b_sn = (K + 1) & ~1LL;
+    if (M == 1 && dd.a_sk != 1) dd.a_sm = 1;
+    if (N == 1 && dd.b_sk != 1) dd.b_sn = 1;
+    d = &dd;
+    const bool a_kc = d->a_sk == 1;
+    const bool a_mc = !a_kc && d->a_sm == 1;
+    const bool b_kc = d->b_sk == 1;
+    const bool b_mc = !b_kc && d->b_sn == 1;
+    bool use_tma = force_path != 2 && (a_kc || a_mc) && (b_kc || b_mc) && batch <= 65535 && load_encode();
+    if (use_tma)
+        use_tma = tma_ok(d->A, a_kc ? d->a_sm : d->a_sk, d->a_sb, batch) && tma_ok(d->B, b_kc ? d->b_sn : d->b_sk, d->b_sb, batch);
+    if (force_path == 1 && !use_tma) return set_error("gemm: TMA path forced but operands are not TMA-describable");
+
+    if (use_tma) {
+        CUtensorMap ta, tb;
+        bool ok;
+        const long long a_bs = batch > 1 ? d->a_sb : 2, b_bs = batch > 1 ? d->b_sb : 2;
+        if (a_kc) ok = make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, BM);
+        else      ok = make_tmap(&ta, d->A, M, K, batch, d->a_sk, a_bs, 16, BK);
+        if (ok) {
+            if (b_kc) ok = make_tmap(&tb, d->B, K, N, batch, d->b_sn, b_bs, BK, BN);
+            else      ok = make_tmap(&tb, d->B, N, K, batch, d->b_sk, b_bs, 16, BK);
+        }
+        if (ok) {
+            GemmParams p;
+            p.M = (int)M; p.N = (int)N; p.K = (int)K;
+            p.tiles_m = (int)((M + BM - 1) / BM);
+            p.tiles_n = (int)((N + BN - 1) / BN);
+            p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb;
+            if (a_kc && b_kc) return launch_tma<true, true>(ta, tb, p, (int)batch, st);
+            if (a_kc && !b_kc) return launch_tma<true, false>(ta, tb, p, (int)batch, st);
+            if (!a_kc && b_kc) return launch_tma<false, true>(ta, tb, p, (int)batch, st);
+            return launch_tma<false, false>(ta, tb, p, (int)batch, st);
+        }
+        if (force_path == 1) return set_error("gemm: cuTensorMapEncodeTiled rejected the operands");
+    }
+    // generic path
+    for (long long b0 = 0; b0 < batch; b0 += 65535) {
+        const long long nb = (batch - b0 < 65535) ? batch - b0 : 65535;
+        dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)nb);
+        gemm_generic_kernel<<<grid, 256, 0, st>>>((int)M, (int)N, (int)K,
+                                                   d->A + b0 * d->a_sb, d->a_sm, d->a_sk, d->a_sb,
+                                                   d->B + b0 * d->b_sb, d->b_sk, d->b_sn, d->b_sb,
+                                                   d->C + b0 * d->c_sb, d->c_sm, d->c_sn, d->c_sb);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error("gemm_generic launch failed: %s", cudaGetErrorString(e));
+        count_launch();
+    }
+    return 0;
+}
+
+}  // namespace adb
+
+extern "C" int adb_gemm_f64(const adb_gemm_desc* desc, void* stream) {
+    return adb::gemm_f64(desc, reinterpret_cast<cudaStream_t>(stream), 0);
+}
+extern "C" int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path) {
+    return adb::gemm_f64(desc, reinterpret_cast<cudaStream_t>(stream), path);
+}
