@@ -1,0 +1,109 @@
+"""Iterative evaluator: walks the DAG post-order and runs each node's device kernel exactly once.
+
+Replaces the recursive `child()` calls inside every reference `_eval` (e.g. autodiff/core/ops.py:173) — same
+memoisation contract as reference node.py:42-46, no recursion limit, values stay in HBM between nodes."""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from ..device import DeviceArray, stream_ptr, to_device, torch
+from .node import Node, Variable
+
+_pending_flags = []   # (torch int32 tensor, exception) raised at the next host synchronisation
+
+
+def _is_device_node(node):
+    if "_eval" in node.__dict__:
+        return False
+    cls_eval = type(node)._eval
+    return cls_eval is Node._eval or isinstance(node, Variable)
+
+
+def _has_value(node):
+    return node._dev is not None or node._host is not None
+
+
+def evaluate(top):
+    stack = [top]
+    while stack:
+        node = stack[-1]
+        if _has_value(node):
+            stack.pop()
+            continue
+        if not _is_device_node(node):
+            # user-defined numpy op (or ad.checkpoint's opaque node): its _eval pulls its own inputs through child()
+            node._host = node._eval()
+            stack.pop()
+            continue
+        pending = [c for c in node.children if not _has_value(c)]
+        if pending:
+            stack.extend(reversed(pending))
+            continue
+        node._dev = node._eval_device()
+        stack.pop()
+
+
+def dev(node):
+    """Device value of an already-evaluated (or leaf) node, uploading a host value if that is all there is."""
+    if node._dev is None:
+        if node._host is not None:
+            node._dev = to_device(np.asarray(node._host))
+        else:
+            evaluate(node)
+            if node._dev is None:
+                node._dev = to_device(np.asarray(node._host))
+    return node._dev
+
+
+def scalar_of(node):
+    """Host-known 0-d constant of a leaf, else None."""
+    if isinstance(node, Variable):
+        return node.host_scalar()
+    return None
+
+
+def add_pending_flag(flag_tensor, exc):
+    _pending_flags.append((flag_tensor, exc))
+
+
+def check_pending_flags():
+    """Called after every device->host synchronisation: surfaces deferred device-side validation errors
+    (SoftmaxCEWithLogits label check, reference ops.py:246-248) as the reference's ValueError."""
+    if not _pending_flags:
+        return
+    flags = list(_pending_flags)
+    del _pending_flags[:]
+    for flag, exc in flags:
+        if int(flag.item()) != 0:
+            raise exc
+
+
+# ------------------------------------------------------------------------------------------- program helper
+def run_program(code, inputs, out_shape, n_out=1):
+    """code: list of (op, arg, imm); inputs: list of DeviceArray; returns the output DeviceArray(s)."""
+    n = len(code)
+    if n > _lib.EW_MAX_INSTR:
+        raise ValueError("elementwise program too long (%d instructions)" % n)
+    prog = (_lib.EwInstr * n)()
+    for i, (op, arg, imm) in enumerate(code):
+        prog[i].op = op
+        prog[i].arg = arg
+        prog[i].imm = imm
+    outs = [DeviceArray.empty(out_shape) for _ in range(n_out)]
+    tin = (_lib.Tensor * max(len(inputs), 1))(*[a.tensor() for a in inputs])
+    tout = (_lib.Tensor * n_out)(*[o.tensor() for o in outs])
+    _lib.check(_lib.lib().adb_ewise(prog, n, len(inputs), tin, n_out, tout, C.c_void_p(stream_ptr())))
+    return outs[0] if n_out == 1 else outs
+
+
+def run_program_into(code, inputs, outs):
+    n = len(code)
+    prog = (_lib.EwInstr * n)()
+    for i, (op, arg, imm) in enumerate(code):
+        prog[i].op = op
+        prog[i].arg = arg
+        prog[i].imm = imm
+    tin = (_lib.Tensor * max(len(inputs), 1))(*[a.tensor() for a in inputs])
+    tout = (_lib.Tensor * len(outs))(*[o.tensor() for o in outs])
+    _lib.check(_lib.lib().adb_ewise(prog, n, len(inputs), tin, len(outs), tout, C.c_void_p(stream_ptr())))

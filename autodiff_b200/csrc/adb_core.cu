@@ -64,6 +64,16 @@ int adb_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream) 
     ADB_CUDA_OK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
     return 0;
 }
+int adb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* host_src, size_t src_pitch, size_t width_bytes, size_t rows, void* stream) {
+    if (!width_bytes || !rows) return 0;
+    ADB_CUDA_OK(cudaMemcpy2DAsync(dst, dst_pitch, host_src, src_pitch, width_bytes, rows, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, void* stream) {
+    if (!width_bytes || !rows) return 0;
+    ADB_CUDA_OK(cudaMemcpy2DAsync(host_dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
 int adb_host_alloc(void** out, size_t bytes) {
     ADB_CUDA_OK(cudaMallocHost(out, bytes ? bytes : 16));
     return 0;

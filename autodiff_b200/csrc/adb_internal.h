@@ -9,6 +9,17 @@ namespace adb {
 int set_error(const char* fmt, ...);   // stores a thread-local message, returns 1
 void count_launch(int n = 1);
 int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path);
+int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out, const adb_tensor* outs,
+              cudaStream_t st);
+struct ReduceSpec {           // dims innermost-first, already collapsed (see reduce.cu)
+    int n_ops, n_o, n_r, group, square;
+    long long odim[4], rdim[4], out_s[4];
+    long long op_os[ADB_RED_MAX_OPS][4], op_rs[ADB_RED_MAX_OPS][4];
+    const double* op[ADB_RED_MAX_OPS];
+    double* out;
+};
+int reduce_run(const ReduceSpec& S, cudaStream_t st);
+int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st);
 }  // namespace adb
 
 #define ADB_CUDA_OK(expr)                                                                 \

@@ -1,0 +1,396 @@
+// Einsum planner (host) — canonicalises a subscript string into one of the device kernels.
+// Replaces `np.einsum(self.op_str, *arr)` at reference autodiff/core/ops.py:180; the subscript grammar
+// follows ops.py:131,167-170 (explicit "->", single-letter indices; "..." is expanded by the host
+// binding before it gets here).
+//
+//   every letter gets an extent and one stride per operand (0 when the operand does not carry it, the
+//   SUM of strides when it carries it twice: diagonals)  =>  out[free] = sum_summed prod_t op_t[...]
+//
+//   no summed letter                      -> ewise product program (broadcast / outer / Hadamard / permute)
+//   2 operands, letters split cleanly into batch | M | N | K groups that each collapse to one stride
+//   and M,N >= 16, K >= 4                -> strided-batched FP64 GEMM (TMA + DMMA)
+//   anything else                         -> sum-of-products reduction kernel (row or column mode)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "adb_internal.h"
+
+namespace adb {
+
+struct Letter {
+    char c;
+    long long extent;
+    bool in_out;
+    long long os;                       // output stride (0 when summed)
+    long long s[ADB_MAX_OPERANDS];      // per-operand stride (0 = absent / broadcast)
+    bool present[ADB_MAX_OPERANDS];     // operand really varies along this letter
+};
+
+struct Problem {
+    int n_ops;
+    std::vector<Letter> letters;        // extent > 1 only
+    const double* op[ADB_MAX_OPERANDS];
+    double* out;
+    bool empty_out;                     // some free extent is 0
+    bool empty_sum;                     // some summed extent is 0
+    adb_tensor out_t;                   // original output view (for fills)
+};
+
+static int parse(const char* op_str, int n_ops, const adb_tensor* ops, const adb_tensor* out, Problem& P) {
+    if (!op_str) return set_error("einsum: null subscripts");
+    if (n_ops < 1 || n_ops > ADB_MAX_OPERANDS) return set_error("einsum: %d operands (max %d)", n_ops, ADB_MAX_OPERANDS);
+    const char* arrow = strstr(op_str, "->");
+    if (!arrow) return set_error("einsum: subscripts '%s' need an explicit '->' (reference ops.py:131)", op_str);
+    std::vector<std::string> subs;
+    {
+        std::string cur;
+        for (const char* p = op_str; p < arrow; ++p) {
+            if (*p == ',') { subs.push_back(cur); cur.clear(); }
+            else if (*p == ' ') continue;
+            else cur.push_back(*p);
+        }
+        subs.push_back(cur);
+    }
+    std::string osub;
+    for (const char* p = arrow + 2; *p; ++p)
+        if (*p != ' ') osub.push_back(*p);
+    if ((int)subs.size() != n_ops) return set_error("Number of operands doesn't match the einsum string!");
+    P.n_ops = n_ops;
+    P.letters.clear();
+    P.empty_out = P.empty_sum = false;
+    P.out = out->ptr;
+    P.out_t = *out;
+    std::vector<Letter> all;
+    auto find = [&](char c) -> Letter* {
+        for (auto& l : all) if (l.c == c) return &l;
+        return nullptr;
+    };
+    for (int t = 0; t < n_ops; ++t) {
+        P.op[t] = ops[t].ptr;
+        if ((int)subs[t].size() != ops[t].rank)
+            return set_error("einsum: operand %d has rank %d but subscripts '%s'", t, ops[t].rank, subs[t].c_str());
+        for (int k = 0; k < ops[t].rank; ++k) {
+            const char c = subs[t][k];
+            if (!((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) return set_error("einsum: bad subscript character '%c'", c);
+            Letter* l = find(c);
+            if (!l) {
+                Letter nl;
+                memset(&nl, 0, sizeof nl);
+                nl.c = c;
+                nl.extent = 1;
+                all.push_back(nl);
+                l = &all.back();
+            }
+            const long long d = ops[t].shape[k];
+            if (d != 1) {
+                if (l->extent != 1 && l->extent != d)
+                    return set_error("einsum: operand %d dim %d has extent %lld but '%c' is already %lld", t, k, d, c, l->extent);
+                l->extent = d;
+                l->s[t] += ops[t].stride[k];
+                l->present[t] = true;
+            }
+        }
+    }
+    if ((int)osub.size() != out->rank) return set_error("einsum: output has rank %d but subscripts '%s'", out->rank, osub.c_str());
+    for (int k = 0; k < out->rank; ++k) {
+        const char c = osub[k];
+        Letter* l = find(c);
+        if (!l) return set_error("einsum: output subscript '%c' never appeared in an input", c);
+        if (l->in_out) return set_error("einsum: output subscript '%c' appears twice", c);
+        l->in_out = true;
+        l->os = out->stride[k];
+        if (out->shape[k] != l->extent)
+            return set_error("einsum: output dim %d has extent %lld, expected %lld", k, (long long)out->shape[k], l->extent);
+    }
+    for (auto& l : all) {
+        if (l.extent == 0) { (l.in_out ? P.empty_out : P.empty_sum) = true; }
+        if (l.extent > 1) P.letters.push_back(l);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int run_fill_zero(const Problem& P, cudaStream_t st, std::string* desc) {
+    if (desc) { *desc = "fill0"; return 0; }
+    adb_ew_instr code[2] = {{ADB_EW_LOAD | ADB_EW_SRC_IMM, 0, 0.0}, {ADB_EW_STORE_OUT, 0, 0.0}};
+    return ewise_run(code, 2, 0, nullptr, 1, &P.out_t, st);
+}
+
+static int run_product(const Problem& P, cudaStream_t st, std::string* desc) {
+    // iteration space = free letters ordered by output stride (outermost first)
+    std::vector<const Letter*> ls;
+    for (auto& l : P.letters) ls.push_back(&l);
+    std::sort(ls.begin(), ls.end(), [](const Letter* a, const Letter* b) { return a->os > b->os; });
+    const int rank = (int)ls.size();
+    if (rank > ADB_MAX_RANK) return set_error("einsum: %d free letters (max %d)", rank, ADB_MAX_RANK);
+    if (desc) {
+        char b[128];
+        snprintf(b, sizeof b, "ewise product ops=%d rank=%d", P.n_ops, rank);
+        *desc = b;
+        return 0;
+    }
+    adb_tensor o;
+    adb_tensor in[ADB_MAX_OPERANDS];
+    o.ptr = P.out; o.rank = rank;
+    for (int k = 0; k < rank; ++k) { o.shape[k] = ls[k]->extent; o.stride[k] = ls[k]->os; }
+    adb_ew_instr code[ADB_MAX_OPERANDS + 1];
+    for (int t = 0; t < P.n_ops; ++t) {
+        in[t].ptr = const_cast<double*>(P.op[t]);
+        in[t].rank = rank;
+        for (int k = 0; k < rank; ++k) {
+            in[t].shape[k] = ls[k]->present[t] ? ls[k]->extent : 1;
+            in[t].stride[k] = ls[k]->present[t] ? ls[k]->s[t] : 0;
+        }
+        code[t].op = (t == 0 ? ADB_EW_LOAD : ADB_EW_MUL) | ADB_EW_SRC_IN;
+        code[t].arg = t;
+        code[t].imm = 0.0;
+    }
+    code[P.n_ops].op = ADB_EW_STORE_OUT; code[P.n_ops].arg = 0; code[P.n_ops].imm = 0.0;
+    return ewise_run(code, P.n_ops + 1, P.n_ops, in, 1, &o, st);
+}
+
+// Collapse a group of letters to (extent, stride per tensor). `key` orders them outermost-first.
+struct Group {
+    long long extent = 1;
+    long long sa = 0, sb = 0, sc = 0;
+    bool ok = true;
+    int count = 0;
+};
+
+static Group collapse_group(std::vector<const Letter*> ls, bool useA, bool useB, bool useC, int ia, int ib) {
+    Group g;
+    g.count = (int)ls.size();
+    if (ls.empty()) return g;
+    auto key = [&](const Letter* l) { return useC ? l->os : l->s[ia]; };
+    std::sort(ls.begin(), ls.end(), [&](const Letter* a, const Letter* b) { return key(a) > key(b); });
+    const Letter* in = ls.back();
+    g.extent = in->extent;
+    g.sa = useA ? in->s[ia] : 0;
+    g.sb = useB ? in->s[ib] : 0;
+    g.sc = useC ? in->os : 0;
+    for (int i = (int)ls.size() - 2; i >= 0; --i) {
+        const Letter* l = ls[i];
+        if (useA && l->s[ia] != g.sa * g.extent) g.ok = false;
+        if (useB && l->s[ib] != g.sb * g.extent) g.ok = false;
+        if (useC && l->os != g.sc * g.extent) g.ok = false;
+        g.extent *= l->extent;
+    }
+    return g;
+}
+
+static bool try_gemm(const Problem& P, adb_gemm_desc& d) {
+    if (P.n_ops != 2) return false;
+    std::vector<const Letter*> B_, M_, N_, K_;
+    for (auto& l : P.letters) {
+        const bool a = l.present[0], b = l.present[1], o = l.in_out;
+        if (a && b && o) B_.push_back(&l);
+        else if (a && !b && o) M_.push_back(&l);
+        else if (!a && b && o) N_.push_back(&l);
+        else if (a && b && !o) K_.push_back(&l);
+        else return false;  // a letter summed out of a single operand: not a plain GEMM
+    }
+    if (M_.empty() || N_.empty() || K_.empty()) return false;
+    Group gm = collapse_group(M_, true, false, true, 0, 1);
+    Group gn = collapse_group(N_, false, true, true, 0, 1);
+    Group gk = collapse_group(K_, true, true, false, 0, 1);
+    Group gb = collapse_group(B_, true, true, true, 0, 1);
+    if (!gm.ok || !gn.ok || !gk.ok || !gb.ok) return false;
+    if (gm.extent < 16 || gn.extent < 16 || gk.extent < 4) return false;
+    if (gm.sa < 0 || gk.sa < 0 || gk.sb < 0 || gn.sb < 0 || gm.sc < 0 || gn.sc < 0) return false;
+    d.batch = gb.extent;
+    d.K = gk.extent;
+    if (gn.sc <= gm.sc) {
+        d.M = gm.extent; d.N = gn.extent;
+        d.A = P.op[0]; d.a_sm = gm.sa; d.a_sk = gk.sa; d.a_sb = gb.sa;
+        d.B = P.op[1]; d.b_sk = gk.sb; d.b_sn = gn.sb; d.b_sb = gb.sb;
+        d.C = P.out; d.c_sm = gm.sc; d.c_sn = gn.sc; d.c_sb = gb.sc;
+    } else {  // output is "N-major": compute the transpose so the fast C stride follows the GEMM n index
+        d.M = gn.extent; d.N = gm.extent;
+        d.A = P.op[1]; d.a_sm = gn.sb; d.a_sk = gk.sb; d.a_sb = gb.sb;
+        d.B = P.op[0]; d.b_sk = gk.sa; d.b_sn = gm.sa; d.b_sb = gb.sa;
+        d.C = P.out; d.c_sm = gn.sc; d.c_sn = gm.sc; d.c_sb = gb.sc;
+    }
+    return true;
+}
+
+static int run_reduce(const Problem& P, cudaStream_t st, std::string* desc) {
+    if (P.n_ops > ADB_RED_MAX_OPS) return set_error("einsum: %d operands with summed letters (max %d)", P.n_ops, ADB_RED_MAX_OPS);
+    // the operand spanning the most elements decides the memory-friendly ordering
+    int big = 0;
+    double big_elems = -1;
+    for (int t = 0; t < P.n_ops; ++t) {
+        double e = 1;
+        for (auto& l : P.letters) if (l.present[t]) e *= (double)l.extent;
+        if (e > big_elems) { big_elems = e; big = t; }
+    }
+    auto stride_key = [&](const Letter* l) -> long long {
+        if (l->present[big]) return l->s[big] < 0 ? -l->s[big] : l->s[big];
+        return (1LL << 60) + (l->os < 0 ? -l->os : l->os);   // letters the big operand lacks go outermost
+    };
+    std::vector<const Letter*> fr, rd;
+    for (auto& l : P.letters) (l.in_out ? fr : rd).push_back(&l);
+    std::sort(fr.begin(), fr.end(), [&](const Letter* a, const Letter* b) { return stride_key(a) < stride_key(b); });
+    std::sort(rd.begin(), rd.end(), [&](const Letter* a, const Letter* b) { return stride_key(a) < stride_key(b); });
+
+    ReduceSpec S;
+    memset(&S, 0, sizeof S);
+    S.n_ops = P.n_ops;
+    for (int t = 0; t < P.n_ops; ++t) S.op[t] = P.op[t];
+    S.out = P.out;
+    // collapse innermost-first lists
+    auto push = [&](const std::vector<const Letter*>& ls, bool is_out, long long* dim, long long (*ops)[4], long long* outs, int& n) -> bool {
+        n = 0;
+        for (const Letter* l : ls) {
+            bool merged = false;
+            if (n > 0) {
+                bool ok = true;
+                for (int t = 0; t < P.n_ops && ok; ++t) ok = (l->present[t] ? l->s[t] : 0) == ops[t][n - 1] * dim[n - 1];
+                if (is_out && ok) ok = l->os == outs[n - 1] * dim[n - 1];
+                if (ok) { dim[n - 1] *= l->extent; merged = true; }
+            }
+            if (!merged) {
+                if (n == 4) return false;
+                dim[n] = l->extent;
+                for (int t = 0; t < P.n_ops; ++t) ops[t][n] = l->present[t] ? l->s[t] : 0;
+                if (is_out) outs[n] = l->os;
+                ++n;
+            }
+        }
+        return true;
+    };
+    if (!push(fr, true, S.odim, S.op_os, S.out_s, S.n_o)) return set_error("einsum: more than 4 non-collapsible output dims");
+    if (!push(rd, false, S.rdim, S.op_rs, nullptr, S.n_r)) return set_error("einsum: more than 4 non-collapsible summed dims");
+
+    // row mode when the big operand's fastest letter is summed, column mode when it is free
+    long long min_free = 1LL << 62, min_red = 1LL << 62;
+    for (const Letter* l : fr) if (l->present[big]) min_free = std::min(min_free, stride_key(l));
+    for (const Letter* l : rd) if (l->present[big]) min_red = std::min(min_red, stride_key(l));
+    S.group = 1;
+    if (min_red < min_free && S.n_r > 0) {
+        if (S.rdim[0] >= 64) S.group = 32;
+        else if (S.rdim[0] >= 8) S.group = 8;
+    }
+    if (desc) {
+        char b[160];
+        long long O = 1, R = 1;
+        for (int k = 0; k < S.n_o; ++k) O *= S.odim[k];
+        for (int k = 0; k < S.n_r; ++k) R *= S.rdim[k];
+        snprintf(b, sizeof b, "reduce ops=%d G=%d O=%lld R=%lld odims=%d rdims=%d", P.n_ops, S.group, O, R, S.n_o, S.n_r);
+        *desc = b;
+        return 0;
+    }
+    return reduce_run(S, st);
+}
+
+static int run_problem(const Problem& P, cudaStream_t st, std::string* desc) {
+    if (P.empty_out) { if (desc) *desc = "empty"; return 0; }
+    if (P.empty_sum) return run_fill_zero(P, st, desc);
+    bool has_sum = false;
+    for (auto& l : P.letters) has_sum |= !l.in_out;
+    if (!has_sum) return run_product(P, st, desc);
+    adb_gemm_desc d;
+    memset(&d, 0, sizeof d);
+    if (try_gemm(P, d)) {
+        if (desc) {
+            char b[256];
+            snprintf(b, sizeof b, "gemm M=%lld N=%lld K=%lld batch=%lld a=(%lld,%lld,%lld) b=(%lld,%lld,%lld) c=(%lld,%lld,%lld)%s",
+                     (long long)d.M, (long long)d.N, (long long)d.K, (long long)d.batch, (long long)d.a_sm, (long long)d.a_sk, (long long)d.a_sb,
+                     (long long)d.b_sk, (long long)d.b_sn, (long long)d.b_sb, (long long)d.c_sm, (long long)d.c_sn, (long long)d.c_sb,
+                     d.A == P.op[1] ? " swapped" : "");
+            *desc = b;
+            return 0;
+        }
+        return gemm_f64(&d, st, 0);
+    }
+    return run_reduce(P, st, desc);
+}
+
+}  // namespace adb
+
+extern "C" {
+
+int adb_einsum(const char* op_str, int n_ops, const adb_tensor* ops, const adb_tensor* out, void* stream) {
+    adb::Problem P;
+    if (int rc = adb::parse(op_str, n_ops, ops, out, P)) return rc;
+    return adb::run_problem(P, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int adb_einsum_describe(const char* op_str, int n_ops, const adb_tensor* ops, const adb_tensor* out, char* buf, size_t buflen) {
+    adb::Problem P;
+    if (int rc = adb::parse(op_str, n_ops, ops, out, P)) return rc;
+    std::string desc;
+    if (int rc = adb::run_problem(P, nullptr, &desc)) return rc;
+    if (buf && buflen) {
+        strncpy(buf, desc.c_str(), buflen - 1);
+        buf[buflen - 1] = 0;
+    }
+    return 0;
+}
+
+// np.sum(x, axis=axes, keepdims=True) — reference reshape.py:14.  Reduced axes are those where out has extent 1.
+int adb_reduce_sum(const adb_tensor* x, const adb_tensor* out, void* stream) {
+    if (x->rank != out->rank) return adb::set_error("reduce_sum: rank mismatch %d vs %d", x->rank, out->rank);
+    adb::Problem P;
+    P.n_ops = 1;
+    P.op[0] = x->ptr;
+    P.out = out->ptr;
+    P.out_t = *out;
+    P.empty_out = P.empty_sum = false;
+    for (int k = 0; k < x->rank; ++k) {
+        const long long d = x->shape[k];
+        const bool keep = out->shape[k] == d;
+        if (!keep && out->shape[k] != 1) return adb::set_error("reduce_sum: out dim %d is %lld, expected %lld or 1", k, (long long)out->shape[k], d);
+        if (d == 0) { (keep ? P.empty_out : P.empty_sum) = true; }
+        if (d <= 1) continue;
+        adb::Letter l;
+        memset(&l, 0, sizeof l);
+        l.c = (char)('a' + k);
+        l.extent = d;
+        l.in_out = keep;
+        l.os = keep ? out->stride[k] : 0;
+        l.s[0] = x->stride[k];
+        l.present[0] = true;
+        P.letters.push_back(l);
+    }
+    return adb::run_problem(P, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+// np.sum(np.square(x)) — reference ops.py:369 (FrobeniusNorm).
+int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* stream) {
+    adb::ReduceSpec S;
+    memset(&S, 0, sizeof S);
+    S.n_ops = 1;
+    S.square = 1;
+    S.op[0] = x->ptr;
+    S.out = out_scalar;
+    // order dims by |stride| ascending and collapse
+    std::vector<int> ax;
+    for (int k = 0; k < x->rank; ++k) {
+        if (x->shape[k] == 0) {
+            adb_tensor o; o.ptr = out_scalar; o.rank = 0;
+            adb_ew_instr code[2] = {{ADB_EW_LOAD | ADB_EW_SRC_IMM, 0, 0.0}, {ADB_EW_STORE_OUT, 0, 0.0}};
+            return adb::ewise_run(code, 2, 0, nullptr, 1, &o, reinterpret_cast<cudaStream_t>(stream));
+        }
+        if (x->shape[k] > 1) ax.push_back(k);
+    }
+    std::sort(ax.begin(), ax.end(), [&](int a, int b) { return llabs(x->stride[a]) < llabs(x->stride[b]); });
+    int n = 0;
+    for (int k : ax) {
+        if (n > 0 && x->stride[k] == S.op_rs[0][n - 1] * S.rdim[n - 1]) { S.rdim[n - 1] *= x->shape[k]; continue; }
+        if (n == 4) return adb::set_error("sum_squares: more than 4 non-collapsible dims");
+        S.rdim[n] = x->shape[k];
+        S.op_rs[0][n] = x->stride[k];
+        ++n;
+    }
+    S.n_r = n;
+    S.n_o = 0;
+    S.group = (n > 0 && S.rdim[0] >= 64) ? 32 : (n > 0 && S.rdim[0] >= 8 ? 8 : 1);
+    return adb::reduce_run(S, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

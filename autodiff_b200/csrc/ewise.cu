@@ -1,0 +1,332 @@
+// Fused elementwise programs for sm_100a — replaces the numpy ufunc call sites of the reference's
+// elementwise `_eval` bodies (autodiff/core/ops.py:53 Add, :75 Mul, :96 Negate, :116 Recipr, :228 ReLU,
+// :274 SigmoidCE, :290 Pow, :309 Log, :339 Exp, :354 Sigmoid, :369 sqrt, :391 NormalDistribution) and the
+// data-movement nodes (reshape.py:35 Concat, :94 Slice, :99-100 scatter, :126-129 Pad) which are the
+// same kernel running the two-instruction program [LOAD_IN 0; STORE_OUT 0].
+//
+// A program is a short accumulator-machine bytecode that REPLAYS THE REFERENCE'S fp64 OPERATION ORDER
+// (1/(x+eps), x*(x>0), left-to-right n-ary sums/products ...), so fused chains stay bit-compatible with
+// the unfused reference up to libm ulp differences.  Each thread evaluates the whole program on 4
+// consecutive elements of the innermost dimension (interpreter overhead amortised 4x, 2x 128-bit
+// loads/stores per operand), operands broadcast through zero strides.  HBM-bound by construction:
+// every operand element is read once and every output element written once.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "adb_internal.h"
+
+namespace adb {
+
+constexpr int EW_RANK = 5;
+constexpr int EW_V = 4;
+constexpr int EW_TEMPS = 8;
+
+struct EwParams {
+    int n_in, n_out, n_instr, _pad;
+    long long dim[EW_RANK];  // dim[0] innermost (collapsed iteration space of the outputs)
+    long long in_stride[ADB_EW_MAX_IN][EW_RANK];
+    long long out_stride[ADB_EW_MAX_OUT][EW_RANK];
+    const double* in[ADB_EW_MAX_IN];
+    double* out[ADB_EW_MAX_OUT];
+    unsigned in_vec, out_vec;  // bit i: 16-byte aligned unit-stride access along dim0 is legal
+    adb_ew_instr code[ADB_EW_MAX_INSTR];
+};
+
+struct V4 {
+    double v[EW_V];
+};
+
+__device__ __forceinline__ V4 load_in(const EwParams& P, int i, long long base, int nvalid) {
+    V4 r;
+    const double* p = P.in[i] + base;
+    const long long s0 = P.in_stride[i][0];
+    if (s0 == 0) {
+        const double x = __ldg(p);
+#pragma unroll
+        for (int e = 0; e < EW_V; ++e) r.v[e] = x;
+    } else if (((P.in_vec >> i) & 1u) && nvalid == EW_V) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int e = 0; e < EW_V; ++e) r.v[e] = (e < nvalid) ? __ldg(p + e * s0) : 0.0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store_out(const EwParams& P, int j, long long base, int nvalid, const V4& a) {
+    double* p = P.out[j] + base;
+    const long long s0 = P.out_stride[j][0];
+    if (((P.out_vec >> j) & 1u) && nvalid == EW_V) {
+        reinterpret_cast<double2*>(p)[0] = make_double2(a.v[0], a.v[1]);
+        reinterpret_cast<double2*>(p)[1] = make_double2(a.v[2], a.v[3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < EW_V; ++e)
+            if (e < nvalid) p[e * s0] = a.v[e];
+    }
+}
+
+#define EW_FOR for (int e = 0; e < EW_V; ++e)
+
+template <int NT>
+__global__ void __launch_bounds__(256, NT <= 2 ? 3 : 1) ewise_kernel(const __grid_constant__ EwParams P) {
+    const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
+    const long long total = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += step) {
+        long long idx[EW_RANK];
+        long long o = w / chunks0;
+        idx[0] = (w - o * chunks0) * EW_V;
+#pragma unroll
+        for (int k = 1; k < EW_RANK; ++k) {
+            const long long d = P.dim[k];
+            if (d == 1) { idx[k] = 0; continue; }
+            const long long qn = o / d;
+            idx[k] = o - qn * d;
+            o = qn;
+        }
+        const long long rem = P.dim[0] - idx[0];
+        const int nvalid = rem >= EW_V ? EW_V : (int)rem;
+
+        V4 acc;
+        V4 t[NT];
+#pragma unroll
+        for (int e = 0; e < EW_V; ++e) acc.v[e] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+#pragma unroll
+            for (int e = 0; e < EW_V; ++e) t[k].v[e] = 0.0;
+
+        for (int pc = 0; pc < P.n_instr; ++pc) {
+            const int op = P.code[pc].op;
+            const int arg = P.code[pc].arg;
+            const double imm = P.code[pc].imm;
+            V4 x;  // second operand for binary ops
+            const int src = op & 3;  // 0 = none/unary, 1 = input tensor, 2 = immediate, 3 = temp
+            if (src == 1) {
+                long long base = 0;
+#pragma unroll
+                for (int k = 0; k < EW_RANK; ++k) base += idx[k] * P.in_stride[arg][k];
+                x = load_in(P, arg, base, nvalid);
+            } else if (src == 2) {
+#pragma unroll
+                EW_FOR x.v[e] = imm;
+            } else if (src == 3) {
+                // temps live in registers: select by a uniform switch, never by dynamic indexing
+#pragma unroll
+                for (int k = 0; k < NT; ++k)
+                    if (arg == k) x = t[k];
+            }
+            switch (op >> 2) {
+                case ADB_EW_LOAD >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = x.v[e];
+                    break;
+                case ADB_EW_ADD >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = acc.v[e] + x.v[e];
+                    break;
+                case ADB_EW_MUL >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = acc.v[e] * x.v[e];
+                    break;
+                case ADB_EW_DIV >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = acc.v[e] / x.v[e];
+                    break;
+                case ADB_EW_POW >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = pow(acc.v[e], x.v[e]);
+                    break;
+                case ADB_EW_RPOW >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = pow(x.v[e], acc.v[e]);
+                    break;
+                case ADB_EW_MAX >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = fmax(acc.v[e], x.v[e]);
+                    break;
+                case ADB_EW_STORE_T >> 2:
+#pragma unroll
+                    for (int k = 0; k < NT; ++k)
+                        if (arg == k) t[k] = acc;
+                    break;
+                case ADB_EW_STORE_OUT >> 2: {
+                    long long base = 0;
+#pragma unroll
+                    for (int k = 0; k < EW_RANK; ++k) base += idx[k] * P.out_stride[arg][k];
+                    store_out(P, arg, base, nvalid, acc);
+                    break;
+                }
+                case ADB_EW_NEG >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = -acc.v[e];
+                    break;
+                case ADB_EW_RECIP_EPS >> 2:  // reference ops.py:116: 1 / (x + eps)
+#pragma unroll
+                    EW_FOR acc.v[e] = 1.0 / (acc.v[e] + imm);
+                    break;
+                case ADB_EW_LOG_EPS >> 2:  // reference ops.py:309: log(x + eps)
+#pragma unroll
+                    EW_FOR acc.v[e] = log(acc.v[e] + imm);
+                    break;
+                case ADB_EW_EXP >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = exp(acc.v[e]);
+                    break;
+                case ADB_EW_RELU >> 2:  // reference ops.py:228: val * (val > 0)
+#pragma unroll
+                    EW_FOR acc.v[e] = acc.v[e] * (acc.v[e] > 0.0 ? 1.0 : 0.0);
+                    break;
+                case ADB_EW_SIGMOID >> 2:  // reference ops.py:354: 1 / (1 + exp(-x))
+#pragma unroll
+                    EW_FOR acc.v[e] = 1.0 / (1.0 + exp(-acc.v[e]));
+                    break;
+                case ADB_EW_SQRT >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = sqrt(acc.v[e]);
+                    break;
+                case ADB_EW_ABS >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = fabs(acc.v[e]);
+                    break;
+                case ADB_EW_SQUARE >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = acc.v[e] * acc.v[e];
+                    break;
+                case ADB_EW_LOG >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = log(acc.v[e]);
+                    break;
+                case ADB_EW_RECIP >> 2:
+#pragma unroll
+                    EW_FOR acc.v[e] = 1.0 / acc.v[e];
+                    break;
+                default:
+                    break;
+            }
+        }
+    }
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Collapse the iteration space: drop size-1 dims, merge adjacent dims that are jointly linear in every tensor.
+int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out, const adb_tensor* outs,
+              cudaStream_t st) {
+    if (n_in < 0 || n_in > ADB_EW_MAX_IN) return set_error("ewise: %d inputs (max %d)", n_in, ADB_EW_MAX_IN);
+    if (n_out < 1 || n_out > ADB_EW_MAX_OUT) return set_error("ewise: %d outputs (max %d)", n_out, ADB_EW_MAX_OUT);
+    if (n_instr < 1 || n_instr > ADB_EW_MAX_INSTR) return set_error("ewise: %d instructions (max %d)", n_instr, ADB_EW_MAX_INSTR);
+    const int rank = outs[0].rank;
+    if (rank < 0 || rank > ADB_MAX_RANK) return set_error("ewise: bad rank %d", rank);
+    for (int j = 1; j < n_out; ++j) {
+        if (outs[j].rank != rank) return set_error("ewise: outputs must share one shape");
+        for (int k = 0; k < rank; ++k)
+            if (outs[j].shape[k] != outs[0].shape[k]) return set_error("ewise: outputs must share one shape");
+    }
+    // validate opcodes / operand indices on the host so the kernel never indexes out of range
+    for (int i = 0; i < n_instr; ++i) {
+        const int op = code[i].op, src = op & 3, arg = code[i].arg;
+        if (op < 0 || (op >> 2) > (ADB_EW_RECIP >> 2)) return set_error("ewise: bad opcode %d at %d", op, i);
+        if (src == 1 && (arg < 0 || arg >= n_in)) return set_error("ewise: instr %d reads input %d of %d", i, arg, n_in);
+        if ((src == 3 || (op >> 2) == (ADB_EW_STORE_T >> 2)) && (arg < 0 || arg >= EW_TEMPS)) return set_error("ewise: instr %d uses temp %d", i, arg);
+        if ((op >> 2) == (ADB_EW_STORE_OUT >> 2) && (arg < 0 || arg >= n_out)) return set_error("ewise: instr %d stores output %d of %d", i, arg, n_out);
+    }
+    // inputs broadcast against the output shape, numpy style (right-aligned)
+    long long shape[ADB_MAX_RANK];
+    long long istr[ADB_EW_MAX_IN][ADB_MAX_RANK];
+    long long ostr[ADB_EW_MAX_OUT][ADB_MAX_RANK];
+    long long total = 1;
+    for (int k = 0; k < rank; ++k) { shape[k] = outs[0].shape[k]; total *= shape[k]; }
+    if (total == 0) return 0;
+    for (int i = 0; i < n_in; ++i) {
+        const int r = ins[i].rank;
+        if (r > rank) return set_error("ewise: input %d has rank %d > output rank %d", i, r, rank);
+        for (int k = 0; k < rank; ++k) {
+            const int ik = k - (rank - r);
+            if (ik < 0) { istr[i][k] = 0; continue; }
+            const long long d = ins[i].shape[ik];
+            if (d == shape[k]) istr[i][k] = (d == 1) ? 0 : ins[i].stride[ik];
+            else if (d == 1) istr[i][k] = 0;
+            else return set_error("ewise: input %d dim %d (%lld) does not broadcast to %lld", i, ik, d, shape[k]);
+        }
+    }
+    for (int j = 0; j < n_out; ++j)
+        for (int k = 0; k < rank; ++k) ostr[j][k] = shape[k] == 1 ? 0 : outs[j].stride[k];
+
+    // collapse, walking from the innermost dim outwards
+    EwParams P;
+    P.n_in = n_in; P.n_out = n_out; P.n_instr = n_instr; P._pad = 0;
+    int nd = 0;
+    for (int k = rank - 1; k >= 0; --k) {
+        if (shape[k] == 1) continue;
+        bool merged = false;
+        if (nd > 0) {
+            const int c = nd - 1;
+            bool ok = true;
+            for (int i = 0; i < n_in && ok; ++i) ok = istr[i][k] == P.in_stride[i][c] * P.dim[c];
+            for (int j = 0; j < n_out && ok; ++j) ok = ostr[j][k] == P.out_stride[j][c] * P.dim[c];
+            if (ok) { P.dim[c] *= shape[k]; merged = true; }
+        }
+        if (!merged) {
+            if (nd == EW_RANK) return set_error("ewise: iteration space does not collapse to %d dims", EW_RANK);
+            P.dim[nd] = shape[k];
+            for (int i = 0; i < n_in; ++i) P.in_stride[i][nd] = istr[i][k];
+            for (int j = 0; j < n_out; ++j) P.out_stride[j][nd] = ostr[j][k];
+            ++nd;
+        }
+    }
+    for (int k = nd; k < EW_RANK; ++k) {
+        P.dim[k] = 1;
+        for (int i = 0; i < n_in; ++i) P.in_stride[i][k] = 0;
+        for (int j = 0; j < n_out; ++j) P.out_stride[j][k] = 0;
+    }
+    P.in_vec = 0; P.out_vec = 0;
+    for (int i = 0; i < n_in; ++i) {
+        P.in[i] = ins[i].ptr;
+        bool v = P.in_stride[i][0] == 1 && (reinterpret_cast<uintptr_t>(ins[i].ptr) & 15) == 0;
+        for (int k = 1; k < EW_RANK && v; ++k) v = (P.in_stride[i][k] & 1) == 0;
+        if (v) P.in_vec |= 1u << i;
+    }
+    for (int j = 0; j < n_out; ++j) {
+        P.out[j] = outs[j].ptr;
+        bool v = P.out_stride[j][0] == 1 && (reinterpret_cast<uintptr_t>(outs[j].ptr) & 15) == 0;
+        for (int k = 1; k < EW_RANK && v; ++k) v = (P.out_stride[j][k] & 1) == 0;
+        if (v) P.out_vec |= 1u << j;
+    }
+    for (int i = 0; i < n_instr; ++i) P.code[i] = code[i];
+
+    const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
+    const long long work = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
+    long long blocks = (work + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;   // 8 resident 256-thread CTAs per SM, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    int max_temp = -1;
+    for (int i = 0; i < n_instr; ++i)
+        if ((code[i].op & 3) == 3 || (code[i].op >> 2) == (ADB_EW_STORE_T >> 2)) max_temp = code[i].arg > max_temp ? code[i].arg : max_temp;
+    if (max_temp < 2) ewise_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(P);
+    else ewise_kernel<EW_TEMPS><<<(unsigned)blocks, 256, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("ewise launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+}  // namespace adb
+
+extern "C" int adb_ewise(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out,
+                         const adb_tensor* outs, void* stream) {
+    return adb::ewise_run(code, n_instr, n_in, ins, n_out, outs, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,303 @@
+// Sum-of-products reductions for sm_100a:  out[o] = sum_r prod_t op_t[o, r]   (1..4 operands, fp64).
+// Replaces np.einsum (reference autodiff/core/ops.py:180) for every form that is NOT a true GEMM —
+// axis sums ('ab->b', 'ijkl->ij', 'i->'), GEMV-like contractions ('ijkl,jl->ik', 'ijkl,ik->jl'), the
+// Softmax denominator ('bi,o->bo') — and np.sum(keepdims) at reshape.py:14 and np.sum(np.square) at
+// ops.py:369.  All of these are HBM-bound: each operand element is read once.
+//
+// One kernel template, parameterised by G = lanes cooperating on one output element:
+//   G = 32 / 8 : the innermost REDUCED index is memory-contiguous -> lanes stride along it (coalesced),
+//                partial sums combined with warp shuffles ("row" reductions).
+//   G = 1      : the innermost OUTPUT index is memory-contiguous -> adjacent threads own adjacent outputs
+//                (coalesced) and walk the reduced indices sequentially ("column" reductions).
+// The reduced index space can be split across gridDim.y; partials go to a workspace and a second tiny
+// kernel adds them in a fixed order (deterministic, no atomics).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "adb_internal.h"
+
+namespace adb {
+
+constexpr int RD = 4;  // max collapsed dims on each side
+
+struct RedParams {
+    int n_ops;
+    int splits;
+    long long O;                 // number of outputs
+    long long odim[RD], rdim[RD];
+    long long op_os[ADB_RED_MAX_OPS][RD], op_rs[ADB_RED_MAX_OPS][RD];
+    long long out_s[RD];
+    const double* op[ADB_RED_MAX_OPS];
+    double* out;
+    double* partial;             // [splits][O] when splits > 1
+    long long router;            // rdim[1]*rdim[2]*rdim[3]
+    long long nblk0;             // inner blocks per outer index
+    long long blk0;              // inner block length
+    long long steps;             // router * nblk0
+    long long steps_per_split;
+    int square;                  // 1: single operand, accumulate x*x (FrobeniusNorm)
+};
+
+template <int G, int NOPS>
+__global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ RedParams P) {
+    constexpr int GROUPS = 256 / G;
+    const int lane = threadIdx.x % G;
+    const long long gstep = (long long)gridDim.x * GROUPS;
+    const int z = blockIdx.y;
+    const long long s_lo = (long long)z * P.steps_per_split;
+    long long s_hi = s_lo + P.steps_per_split;
+    if (s_hi > P.steps) s_hi = P.steps;
+
+    for (long long o = (long long)blockIdx.x * GROUPS + threadIdx.x / G; o < P.O; o += gstep) {
+        long long rem = o;
+        long long base[NOPS];
+#pragma unroll
+        for (int t = 0; t < NOPS; ++t) base[t] = 0;
+        long long out_off = 0;
+#pragma unroll
+        for (int k = 0; k < RD; ++k) {
+            const long long d = P.odim[k];
+            long long i = 0;
+            if (d > 1) { const long long qn = rem / d; i = rem - qn * d; rem = qn; }
+#pragma unroll
+            for (int t = 0; t < NOPS; ++t) base[t] += i * P.op_os[t][k];
+            out_off += i * P.out_s[k];
+        }
+        double acc = 0.0;
+        // position of the first step of this split in (outer multi-index, inner block)
+        long long s = s_lo;
+        long long outer = s / P.nblk0;
+        long long blk = s - outer * P.nblk0;
+        long long ri[RD];
+        {
+            long long r2 = outer;
+#pragma unroll
+            for (int k = 1; k < RD; ++k) {
+                const long long d = P.rdim[k];
+                long long i = 0;
+                if (d > 1) { const long long qn = r2 / d; i = r2 - qn * d; r2 = qn; }
+                ri[k] = i;
+            }
+        }
+        for (; s < s_hi; ++s) {
+            long long roff[NOPS];
+#pragma unroll
+            for (int t = 0; t < NOPS; ++t) {
+                roff[t] = base[t];
+#pragma unroll
+                for (int k = 1; k < RD; ++k) roff[t] += ri[k] * P.op_rs[t][k];
+            }
+            const long long c_lo = blk * P.blk0;
+            long long c_hi = c_lo + P.blk0;
+            if (c_hi > P.rdim[0]) c_hi = P.rdim[0];
+            long long c = c_lo + lane;
+            // 4-way unrolled so several loads are in flight per lane
+            for (; c + 3 * G < c_hi; c += 4 * G) {
+                double pr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long cc = c + u * G;
+                    double v = __ldg(P.op[0] + roff[0] + cc * P.op_rs[0][0]);
+                    if (NOPS == 1 && P.square) v = v * v;
+#pragma unroll
+                    for (int t = 1; t < NOPS; ++t) v *= __ldg(P.op[t] + roff[t] + cc * P.op_rs[t][0]);
+                    pr[u] = v;
+                }
+                acc += pr[0]; acc += pr[1]; acc += pr[2]; acc += pr[3];
+            }
+            for (; c < c_hi; c += G) {
+                double v = __ldg(P.op[0] + roff[0] + c * P.op_rs[0][0]);
+                if (NOPS == 1 && P.square) v = v * v;
+#pragma unroll
+                for (int t = 1; t < NOPS; ++t) v *= __ldg(P.op[t] + roff[t] + c * P.op_rs[t][0]);
+                acc += v;
+            }
+            // advance (blk, ri[1..]) odometer
+            if (++blk == P.nblk0) {
+                blk = 0;
+#pragma unroll
+                for (int k = 1; k < RD; ++k) {
+                    if (++ri[k] < P.rdim[k]) break;
+                    ri[k] = 0;
+                }
+            }
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, G);
+        }
+        if (lane == 0) {
+            if (P.splits == 1) P.out[out_off] = acc;
+            else P.partial[(long long)z * P.O + o] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_finalize_kernel(const __grid_constant__ RedParams P) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < P.O; o += step) {
+        long long rem = o, out_off = 0;
+#pragma unroll
+        for (int k = 0; k < RD; ++k) {
+            const long long d = P.odim[k];
+            long long i = 0;
+            if (d > 1) { const long long qn = rem / d; i = rem - qn * d; rem = qn; }
+            out_off += i * P.out_s[k];
+        }
+        double acc = 0.0;
+        for (int z = 0; z < P.splits; ++z) acc += P.partial[(long long)z * P.O + o];
+        P.out[out_off] = acc;
+    }
+}
+
+template <int G>
+static void launch_reduce(const RedParams& P, dim3 grid, cudaStream_t st) {
+    switch (P.n_ops) {
+        case 1: reduce_kernel<G, 1><<<grid, 256, 0, st>>>(P); break;
+        case 2: reduce_kernel<G, 2><<<grid, 256, 0, st>>>(P); break;
+        case 3: reduce_kernel<G, 3><<<grid, 256, 0, st>>>(P); break;
+        default: reduce_kernel<G, 4><<<grid, 256, 0, st>>>(P); break;
+    }
+}
+
+// dims are given innermost-first and already collapsed by the planner.
+int reduce_run(const ReduceSpec& S, cudaStream_t st) {
+    if (S.n_ops < 1 || S.n_ops > ADB_RED_MAX_OPS) return set_error("reduce: %d operands (max %d)", S.n_ops, ADB_RED_MAX_OPS);
+    RedParams P;
+    P.n_ops = S.n_ops;
+    P.square = S.square;
+    P.O = 1;
+    long long R = 1;
+    for (int k = 0; k < RD; ++k) {
+        P.odim[k] = k < S.n_o ? S.odim[k] : 1;
+        P.rdim[k] = k < S.n_r ? S.rdim[k] : 1;
+        P.out_s[k] = k < S.n_o ? S.out_s[k] : 0;
+        P.O *= P.odim[k];
+        R *= P.rdim[k];
+        for (int t = 0; t < S.n_ops; ++t) {
+            P.op_os[t][k] = k < S.n_o ? S.op_os[t][k] : 0;
+            P.op_rs[t][k] = k < S.n_r ? S.op_rs[t][k] : 0;
+        }
+    }
+    for (int t = 0; t < S.n_ops; ++t) P.op[t] = S.op[t];
+    P.out = S.out;
+    if (P.O == 0) return 0;
+    const int G = S.group;
+    if (G != 1 && G != 8 && G != 32) return set_error("reduce: bad group %d", G);
+    P.router = P.rdim[1] * P.rdim[2] * P.rdim[3];
+    P.blk0 = (long long)G * 16;                       // inner block: 16 elements per lane
+    if (G == 1) P.blk0 = 64;
+    P.nblk0 = (P.rdim[0] + P.blk0 - 1) / P.blk0;
+    if (P.nblk0 < 1) P.nblk0 = 1;
+    P.steps = P.router * P.nblk0;
+
+    const int sms = 148;
+    const long long groups_per_block = 256 / G;
+    long long blocks_x = (P.O + groups_per_block - 1) / groups_per_block;
+    const long long target_blocks = (long long)sms * 8;
+    long long splits = 1;
+    if (blocks_x < target_blocks && R >= 4096) {
+        splits = target_blocks / blocks_x;
+        const long long min_steps = (G == 1) ? 4 : 2;     // keep every split busy for a while
+        if (splits > P.steps / min_steps) splits = P.steps / min_steps;
+        if (splits > 1024) splits = 1024;
+        if (splits < 1) splits = 1;
+    }
+    if (blocks_x > target_blocks * 4) blocks_x = target_blocks * 4;  // grid-stride beyond
+    P.steps_per_split = (P.steps + splits - 1) / splits;
+    splits = (P.steps + P.steps_per_split - 1) / P.steps_per_split;
+    P.splits = (int)splits;
+    P.partial = nullptr;
+    if (splits > 1) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&P.partial), (size_t)splits * P.O * sizeof(double), st);
+        if (e != cudaSuccess) return set_error("reduce: workspace allocation failed: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)blocks_x, (unsigned)splits, 1);
+    if (G == 32) launch_reduce<32>(P, grid, st);
+    else if (G == 8) launch_reduce<8>(P, grid, st);
+    else launch_reduce<1>(P, grid, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("reduce launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    if (splits > 1) {
+        long long fb = (P.O + 255) / 256;
+        if (fb > sms * 8) fb = sms * 8;
+        reduce_finalize_kernel<<<(unsigned)fb, 256, 0, st>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error("reduce finalize launch failed: %s", cudaGetErrorString(e));
+        count_launch();
+        cudaFreeAsync(P.partial, st);
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- SoftmaxCEWithLogits
+// reference ops.py:243-255 — one warp per row:
+//   lse = max + log(sum(exp(z - max)));  out = -sum(l*z - l*lse);  flag if !allclose(sum(l), 1)
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const double* __restrict__ labels, long long l_sr, long long l_sc,
+                                                         const double* __restrict__ logits, long long z_sr, long long z_sc,
+                                                         double* __restrict__ out, long long o_s, long long rows, long long cols,
+                                                         int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const long long wstep = (long long)gridDim.x * 8;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstep) {
+        const double* z = logits + r * z_sr;
+        const double* l = labels + r * l_sr;
+        double mx = -INFINITY;
+        bool nan_seen = false;
+        for (long long c = lane; c < cols; c += 32) {
+            const double v = __ldg(z + c * z_sc);
+            nan_seen |= (v != v);
+            mx = fmax(mx, v);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (__any_sync(0xffffffffu, nan_seen)) mx = NAN;      // np.max propagates NaN
+        double se = 0.0, lsum = 0.0;
+        for (long long c = lane; c < cols; c += 32) {
+            se += exp(__ldg(z + c * z_sc) - mx);
+            lsum += __ldg(l + c * l_sc);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, off);
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        }
+        const double lse = mx + log(se);
+        double s = 0.0;
+        for (long long c = lane; c < cols; c += 32) {
+            const double lv = __ldg(l + c * l_sc);
+            s += lv * __ldg(z + c * z_sc) - lv * lse;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) {
+            out[r * o_s] = -s;
+            // np.allclose(a, 1): |a - 1| <= atol + rtol*|1| with atol=1e-8, rtol=1e-5; NaN fails
+            if (!(fabs(lsum - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+        }
+    }
+}
+
+int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st) {
+    if (labels->rank != 2 || logits->rank != 2) return set_error("softmax_ce: labels and logits must be 2-D (got %d, %d)", labels->rank, logits->rank);
+    const long long rows = logits->shape[0], cols = logits->shape[1];
+    if (labels->shape[0] != rows || labels->shape[1] != cols) return set_error("softmax_ce: labels %lldx%lld vs logits %lldx%lld", (long long)labels->shape[0], (long long)labels->shape[1], rows, cols);
+    if (out->rank != 1 || out->shape[0] != rows) return set_error("softmax_ce: out must have %lld elements", rows);
+    if (rows == 0) return 0;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    softmax_ce_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels->ptr, labels->stride[0], labels->stride[1], logits->ptr, logits->stride[0],
+                                                        logits->stride[1], out->ptr, out->stride[0], rows, cols, flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("softmax_ce launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+}  // namespace adb
+
+extern "C" int adb_softmax_ce(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, void* stream) {
+    return adb::softmax_ce_run(labels, logits, out, flag, reinterpret_cast<cudaStream_t>(stream));
+}

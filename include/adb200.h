@@ -14,12 +14,19 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define ADB_API __attribute__((visibility("default")))
+#else
+#define ADB_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
 #define ADB_MAX_RANK 8
 #define ADB_MAX_OPERANDS 8
+#define ADB_RED_MAX_OPS 4   /* operands of an einsum that still has summed letters and is not a GEMM */
 
 /* A strided fp64 tensor view.  rank 0 = scalar (one element at ptr). Stride 0 = broadcast. */
 typedef struct adb_tensor {
@@ -39,24 +46,93 @@ typedef struct adb_gemm_desc {
 } adb_gemm_desc;
 
 /* ---- library ---------------------------------------------------------------------------------- */
-int adb_init(int device);                    /* cudaSetDevice + driver entry points; call once per process */
-const char* adb_last_error(void);            /* thread-local message of the last failing call */
-const char* adb_version(void);
-int64_t adb_launch_count(void);              /* kernels launched by this library so far (bench.py gpu_launches) */
-int adb_sync(void* stream);                  /* cudaStreamSynchronize */
+ADB_API int adb_init(int device);                    /* cudaSetDevice + driver entry points; call once per process */
+ADB_API const char* adb_last_error(void);            /* thread-local message of the last failing call */
+ADB_API const char* adb_version(void);
+ADB_API int64_t adb_launch_count(void);              /* kernels launched by this library so far (bench.py gpu_launches) */
+ADB_API int adb_sync(void* stream);                  /* cudaStreamSynchronize */
 
 /* ---- memory: replaces numpy array ownership (reference node.py:111-129 Variable._value) --------- */
-int adb_malloc(void** out, size_t bytes, void* stream);          /* stream-ordered pool allocation */
-int adb_free(void* ptr, void* stream);
-int adb_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream);
-int adb_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream);
-int adb_host_alloc(void** out, size_t bytes);                    /* pinned host staging */
-int adb_host_free(void* ptr);
+ADB_API int adb_malloc(void** out, size_t bytes, void* stream);          /* stream-ordered pool allocation */
+ADB_API int adb_free(void* ptr, void* stream);
+ADB_API int adb_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream);
+ADB_API int adb_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream);
+ADB_API int adb_host_alloc(void** out, size_t bytes);                    /* pinned host staging */
+ADB_API int adb_host_free(void* ptr);
+/* pitched copies: `width_bytes` per row, `rows` rows; pitches in bytes (host side may be a strided numpy view) */
+ADB_API int adb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* host_src, size_t src_pitch, size_t width_bytes, size_t rows, void* stream);
+ADB_API int adb_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, void* stream);
 
 /* ---- contraction: replaces np.einsum at reference autodiff/core/ops.py:180 ---------------------- */
-int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
+ADB_API int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
 /* path: 0 = auto, 1 = force TMA+DMMA kernel (error if not describable), 2 = force generic kernel */
-int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
+ADB_API int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
+
+
+/* ---- fused elementwise programs: replace the ufunc bodies of reference autodiff/core/ops.py
+ *      (:53 Add, :75 Mul, :96 Negate, :116 Recipr, :228 ReLU, :274 SigmoidCE, :290 Pow, :309 Log, :339 Exp,
+ *      :354 Sigmoid, :369 sqrt, :391 NormalDistribution) and the copies of reshape.py (:35 Concat,
+ *      :94 Slice, :99-100 scatter, :126-129 Pad).
+ *  Accumulator machine: `acc` plus 8 temps, evaluated per element.  op = KIND | SRC where SRC says where
+ *  the second operand x comes from.  Inputs broadcast numpy-style against the (shared) output shape. */
+#define ADB_EW_MAX_IN 8
+#define ADB_EW_MAX_OUT 4
+#define ADB_EW_MAX_INSTR 64
+#define ADB_EW_SRC_NONE 0
+#define ADB_EW_SRC_IN 1    /* x = input tensor `arg`            */
+#define ADB_EW_SRC_IMM 2   /* x = `imm`                          */
+#define ADB_EW_SRC_TMP 3   /* x = temp `arg`                     */
+enum {
+    ADB_EW_LOAD = 0 << 2,       /* acc = x                          */
+    ADB_EW_ADD = 1 << 2,        /* acc = acc + x                    */
+    ADB_EW_MUL = 2 << 2,        /* acc = acc * x                    */
+    ADB_EW_DIV = 3 << 2,        /* acc = acc / x                    */
+    ADB_EW_POW = 4 << 2,        /* acc = pow(acc, x)                */
+    ADB_EW_RPOW = 5 << 2,       /* acc = pow(x, acc)                */
+    ADB_EW_MAX = 6 << 2,        /* acc = fmax(acc, x)               */
+    ADB_EW_STORE_T = 7 << 2,    /* temp[arg] = acc                  */
+    ADB_EW_STORE_OUT = 8 << 2,  /* out[arg][...] = acc              */
+    ADB_EW_NEG = 9 << 2,        /* acc = -acc                       */
+    ADB_EW_RECIP_EPS = 10 << 2, /* acc = 1 / (acc + imm)   ops.py:116 */
+    ADB_EW_LOG_EPS = 11 << 2,   /* acc = log(acc + imm)    ops.py:309 */
+    ADB_EW_EXP = 12 << 2,
+    ADB_EW_RELU = 13 << 2,      /* acc = acc * (acc > 0)   ops.py:228 */
+    ADB_EW_SIGMOID = 14 << 2,   /* acc = 1 / (1 + exp(-acc)) ops.py:354 */
+    ADB_EW_SQRT = 15 << 2,
+    ADB_EW_ABS = 16 << 2,
+    ADB_EW_SQUARE = 17 << 2,
+    ADB_EW_LOG = 18 << 2,
+    ADB_EW_RECIP = 19 << 2      /* acc = 1 / acc                    */
+};
+typedef struct adb_ew_instr {
+    int32_t op;
+    int32_t arg;
+    double imm;
+} adb_ew_instr;
+ADB_API int adb_ewise(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out,
+              const adb_tensor* outs, void* stream);
+
+/* ---- einsum: replaces np.einsum(self.op_str, *arr) at reference autodiff/core/ops.py:180 ----------
+ *  op_str uses single letters [a-zA-Z] with an explicit "->" (the host expands "..." first, mirroring
+ *  ops.py:131,167-170).  The planner canonicalises the subscripts into one of: alias-free copy/permute,
+ *  broadcast product (no summed letter), reduction (warp-shuffle rows / tiled columns), or
+ *  strided-batched FP64 GEMM on DMMA tensor cores; >2 operands with summed letters are contracted by the
+ *  reduction kernel directly.  `out` must be preallocated with the einsum's result shape. */
+ADB_API int adb_einsum(const char* op_str, int n_ops, const adb_tensor* ops, const adb_tensor* out, void* stream);
+/* Host-only: writes a one-line description of the plan adb_einsum would run ("gemm M=.. N=.. K=.. batch=..",
+ * "reduce rows ...", "ewise ...") into buf.  Needs no GPU; used by the CPU tests of the planner. */
+ADB_API int adb_einsum_describe(const char* op_str, int n_ops, const adb_tensor* ops, const adb_tensor* out, char* buf, size_t buflen);
+
+/* ---- reductions: replace np.sum(x, axis, keepdims=True) at reshape.py:14 (ReduceSumKeepDims) and
+ *      np.sum(np.square(x)) at ops.py:369 (FrobeniusNorm); expressed through the same reduction kernels
+ *      as single-operand einsums.  out has x's rank with size-1 dims on the reduced axes. */
+ADB_API int adb_reduce_sum(const adb_tensor* x, const adb_tensor* out, void* stream);
+ADB_API int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* stream);
+
+/* ---- SoftmaxCEWithLogits._eval, reference ops.py:243-255.  labels/logits: (rows, cols) views;
+ *      out: rows elements (stride out_stride).  *flag (device int) is OR-ed with 1 when a label row does
+ *      not sum to 1 within np.allclose tolerance (ops.py:246-248); the host raises ValueError. */
+ADB_API int adb_softmax_ce(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, void* stream);
 
 #ifdef __cplusplus
 }

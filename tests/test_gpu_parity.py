@@ -1,0 +1,294 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path vs (a) golden vectors produced by the real reference and
+(b) the numpy oracle on fresh seeded inputs.  Tolerance: norm-wise relative error <= 1e-12 in fp64
+(BASELINE.json north_star); integer/index-like results (shapes, flags) exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import oracle.np_autodiff as onp
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ad():
+    import autodiff_b200 as ad
+    ad.init()
+    return ad
+
+
+def rel_err(x, ref):
+    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    x = np.broadcast_to(x, ref.shape) if x.shape != ref.shape and x.size == 1 else x
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0
+    scale = np.max(np.abs(ref))
+    return float(np.max(np.abs(x - ref)) / (scale if scale > 0 else 1.0))
+
+
+def check(x, ref, tol=TOL, what=""):
+    e = rel_err(x, ref)
+    assert e <= tol, "%s rel err %.3e > %.1e" % (what, e, tol)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_case_against_reference_golden(name, ad):
+    gold = np.load(os.path.join(GOLD, "cases.npz"))
+    nodes = cases.derive(ad, name)
+    for key, node in nodes.items():
+        check(node(), gold[name + "/" + key], what=name + "/" + key)
+
+
+def test_readme_numbers(ad):
+    g, wrt = cases.CASES["readme_scalar"](ad)
+    assert abs(float(g()) - 415.4287934927351) <= 1e-12 * 415.4287934927351
+    assert abs(float(ad.grad(g, [wrt[0]])[0]()) - 407.4287934927351) <= 1e-12 * 407.4287934927351
+
+
+def test_tanh_derivatives(ad):
+    gold = np.load(os.path.join(GOLD, "tanh_derivs.npz"))
+    for i, n in enumerate(cases.tanh_derivatives(ad)):
+        check(n(), gold["d%d" % i], what="tanh d%d" % i)
+
+
+def test_mlp_training_steps(ad):
+    gold = np.load(os.path.join(GOLD, "mlp_steps.npz"))
+    hist, weights = cases.mlp_train_steps(ad)
+    for s, h in enumerate(hist):
+        check(h["cost"], gold["step%d/cost" % s], what="cost")
+        check(h["gnorm"], gold["step%d/gnorm" % s], what="gnorm")
+        for i, g in enumerate(h["grads"]):
+            check(g, gold["step%d/grad%d" % (s, i)], what="grad")
+    for i, w in enumerate(weights):
+        check(w, gold["final/w%d" % i], what="weights")
+
+
+def test_char_rnn_second_order(ad):
+    gold = np.load(os.path.join(GOLD, "char_rnn.npz"))
+    total, params = cases.char_rnn_graph(ad)
+    g1 = ad.grad(total, params)
+    check(total(), gold["loss"], what="loss")
+    for i, g in enumerate(g1):
+        check(g(), gold["g%d" % i], what="g%d" % i)
+    check(ad.grad(g1[0], [params[0]])[0](), gold["gg_w"], what="gg")
+
+
+# ----------------------------------------------------------------------------- vs oracle on fresh inputs
+SWEEP = [
+    ("ij,jk->ik", [(300, 260), (260, 140)]),
+    ("ij,jk->ik", [(129, 131), (131, 127)]),                 # odd everything: pitched rows, ragged tiles
+    ("bij,bjk->bik", [(5, 130, 70), (5, 70, 90)]),
+    ("ijkl,jl->ik", [(12, 10, 14, 16), (10, 16)]),
+    ("ijkl,jl->ik", [(20, 8, 24, 70), (8, 70)]),
+]
+
+
+@pytest.mark.parametrize("spec,shapes", SWEEP)
+def test_einsum_forward_and_grads_vs_oracle(spec, shapes, ad):
+    rng = np.random.default_rng(7)
+    vals = [rng.standard_normal(s) for s in shapes]
+    outs = {}
+    for mod in (onp, ad):
+        vs = [mod.Variable(v.copy(), name="v%d" % i) for i, v in enumerate(vals)]
+        e = mod.Einsum(spec, *vs)
+        g = mod.grad(e, vs)
+        outs[mod] = [np.array(e())] + [np.array(x()) for x in g]
+    for a, b in zip(outs[ad], outs[onp]):
+        check(a, b, what=spec)
+
+
+EINSUM_FORMS = [
+    ("ab->b", [(70, 300)]), ("ab->a", [(70, 300)]), ("ab->", [(70, 300)]), ("i->", [(100003,)]), ("ab->ba", [(33, 65)]),
+    ("ijkl->ijk", [(3, 4, 5, 70)]), ("ijkl->ij", [(3, 4, 5, 70)]), ("ijkl->l", [(3, 4, 5, 70)]), ("ijkl->jl", [(3, 4, 5, 70)]),
+    ("bi,o->bo", [(64, 10), (1,)]), ("i,bo,o->bi", [(10,), (64, 1), (1,)]), ("ik,jl->ijkl", [(6, 7), (5, 9)]),
+    ("ijkl,ik->jl", [(6, 5, 7, 9), (6, 7)]), ("bi,bij->bij", [(9, 5), (9, 5, 4)]), ("ij,ij->ij", [(9, 5), (9, 5)]),
+    ("ij,ij->", [(9, 5), (9, 5)]), ("dt,tp,pr->dtp", [(2, 3), (3, 5), (5, 5)]), ("dt,tp->d", [(20, 30), (30, 50)]),
+    ("ii->i", [(7, 7)]), ("ii->", [(7, 7)]), ("i,i->", [(50000,), (50000,)]), ("ij,j->i", [(300, 257), (257,)]),
+    ("i,->i", [(11,), ()]), ("ij,jk->ki", [(40, 50), (50, 60)]), ("bij,bjk->ikb", [(3, 40, 50), (3, 50, 60)]),
+]
+
+
+@pytest.mark.parametrize("spec,shapes", EINSUM_FORMS)
+def test_einsum_forms_vs_numpy(spec, shapes, ad):
+    rng = np.random.default_rng(11)
+    vals = [rng.standard_normal(s) for s in shapes]
+    ref = np.einsum(spec, *vals)
+    got = ad.Einsum(spec, *[ad.Variable(v, name="v") for v in vals])()
+    check(got, ref, what=spec)
+
+
+def test_einsum_on_noncontiguous_operands(ad):
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((40, 6, 50))
+    a = big[:, 2, :]                         # strided view, like Variable(x[:, t, :]) in examples/char_rnn.py:55
+    b = rng.standard_normal((60, 50)).T      # transposed view
+    check(ad.Einsum("ij,jk->ik", ad.Variable(a, name="a"), ad.Variable(b, name="b"))(), a @ b)
+    t = ad.Transpose(ad.Variable(a, name="a"))
+    check((t @ ad.Variable(a, name="a2"))(), a.T @ a)
+    check(ad.Variable(big, name="big")[::-2, 1:5:2, ::3](), big[::-2, 1:5:2, ::3])
+
+
+def test_elementwise_ops_vs_oracle(ad):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((37, 53)); y = rng.random((37, 53)) + 0.5; b = rng.standard_normal(53); c = rng.standard_normal((37, 1))
+
+    def graphs(m):
+        X, Y, B, Cc = (m.Variable(v.copy(), name=n) for v, n in ((x, "x"), (y, "y"), (b, "b"), (c, "c")))
+        return [X + Y + B + Cc + 3, X * Y * B * Cc * 0.5, X - Y, X / Y, 2 / Y, -X, m.Recipr(Y), m.Exp(X), m.Log(Y), m.ReLU(X),
+                m.Sigmoid(X), m.Tanh(X), m.Pow(Y, X), Y ** 2.5, m.Pow(2.0, X), m.SquaredDifference(X, Y), m.Identity(X),
+                m.NormalDistribution(X, 0.3, 1.7), m.SigmoidCEWithLogits(labels=Y, logits=X), m.Softmax(X), m.FrobeniusNorm(X, Y, B),
+                m.ReduceSumKeepDims(X, axes=[0]), m.ReduceSumKeepDims(X, axes=[1]), m.ReduceSumKeepDims(X, axes=[0, 1]),
+                m.Concat(X, Y, axis=0), m.Concat(X, Cc, axis=1), m.Reshape(X, (53, 37)), m.Reshape(X, (-1,)), X[3:30:2, ::-1], X[5],
+                m.Pad(X, [[1, 2], [3, 0]], constant_values=0), m.Transpose(X) @ Y, m.Add(X, X, X), m.Mul(X, X)]
+    for i, (g, r) in enumerate(zip(graphs(ad), graphs(onp))):
+        check(g(), r(), what="graph %d" % i)
+
+
+def test_large_elementwise_and_reduction_shapes(ad):
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((1031, 1027)); y = rng.standard_normal((1031, 1027)); b = rng.standard_normal(1027)
+    X, Y, B = ad.Variable(x, name="x"), ad.Variable(y, name="y"), ad.Variable(b, name="b")
+    check((X * Y + B)(), x * y + b)
+    check(ad.Einsum("ab->b", X)(), x.sum(0))
+    check(ad.Einsum("ab->a", X)(), x.sum(1))
+    check(ad.Einsum("ab->", X)(), x.sum())
+    check(ad.Tanh(X)(), onp.Tanh(onp.Variable(x, name="x"))())
+
+
+def test_softmax_ce_matches_and_validates_labels(ad):
+    rng = np.random.default_rng(2)
+    z = rng.standard_normal((33, 17)) * 5
+    lab = rng.random((33, 17)); lab /= lab.sum(1, keepdims=True)
+    got = ad.SoftmaxCEWithLogits(labels=ad.Variable(lab, name="l"), logits=ad.Variable(z, name="z"))()
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    check(got, ref)
+    bad = lab.copy(); bad[4] *= 1.5
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        ad.SoftmaxCEWithLogits(labels=ad.Variable(bad, name="l"), logits=ad.Variable(z, name="z"))()
+
+
+def test_cached_protocol_finite_difference_style(ad):
+    """The reference's checker edits `var.cached` in place and resets caches (tests/numerical_check.py:5-27)."""
+    rng = np.random.default_rng(4)
+    wv = rng.standard_normal((4, 3))
+    w = ad.Variable(wv.copy(), name="w")
+    graph = ad.Sigmoid(w @ ad.Variable(rng.standard_normal((3, 2)), name="u"))
+    base = graph().copy()
+
+    def uncache(n):
+        n.cached = None
+        for c in n.children:
+            uncache(c)
+    old = w().copy()
+    uncache(graph)
+    w.cached = old
+    w.cached[1, 2] += 0.5
+    moved = graph().copy()
+    assert np.max(np.abs(moved - base)) > 1e-3
+    uncache(graph)
+    check(graph(), base)            # Variable falls back to its own value again
+    # numerical gradient agrees with backprop at the reference's own tolerance
+    gb = ad.grad(graph, [w])[0]()
+    eps, num = 1e-6, np.zeros_like(wv)
+    for idx in np.ndindex(*wv.shape):
+        for sgn in (1, -1):
+            uncache(graph)
+            w.cached = wv.copy()
+            w.cached[idx] += sgn * eps
+            num[idx] += sgn * np.sum(graph()) / (2 * eps)
+    np.testing.assert_allclose(gb, num, rtol=1e-2, atol=1e-5)
+
+
+def test_user_defined_numpy_node_and_checkpoint(ad):
+    class Cube(ad.Node):                       # README: "easy to add your own operations"
+        def __init__(self, node):
+            super().__init__([node], "Cube")
+            self.node = self.children[0]
+            self.shape = self.node.shape
+
+        def _eval(self):
+            return self.node() ** 3
+
+        def _partial_derivative(self, wrt, previous_grad):
+            return previous_grad * 3 * self.node * self.node if wrt == self.node else 0
+    xv = np.linspace(-2, 2, 11)
+    x = ad.Variable(xv, name="x")
+    y = ad.Exp(Cube(x * 2))
+    check(y(), np.exp((xv * 2) ** 3))
+    check(ad.grad(y, [x])[0](), np.exp((xv * 2) ** 3) * 3 * (2 * xv) ** 2 * 2, tol=1e-11)
+
+    def block(a):
+        return ad.Tanh(a) * a
+    c = ad.checkpoint(block)(x)
+    check(c(), block(onp.Variable(xv, name="x")) () if False else onp.Tanh(onp.Variable(xv, name="x"))() * xv)
+    ox = onp.Variable(xv, name="x")
+    check(ad.grad(c, [x])[0](), onp.grad(onp.Tanh(ox) * ox, [ox])[0]())
+
+
+def test_device_resident_variables_and_optimizers(ad):
+    rng = np.random.default_rng(8)
+    p0 = rng.standard_normal((33, 9)); g0 = rng.standard_normal((33, 9))
+    for name, mk in (("sgd", lambda m: m.SGDOptimizer(lr=0.1)), ("mom", lambda m: m.Momentum(1, lr=0.1)),
+                     ("adagrad", lambda m: m.Adagrad(1, lr=0.1)), ("adam", lambda m: m.Adam(1, lr=0.1))):
+        o_ref, o_dev = mk(onp), mk(ad)
+        pr, pd = [p0.copy()], [ad.to_device(p0)]
+        for step in range(3):
+            g = g0 * (step + 1)
+            pr = o_ref([pr[0]], [g])
+            pd = o_dev([pd[0]], [ad.to_device(g)])
+            assert isinstance(pd[0], ad.DeviceArray)
+            check(ad.to_host(pd[0]), pr[0], what="%s step %d" % (name, step))
+    v = ad.Variable(ad.to_device(p0), name="dev")
+    check((v * 2)(), p0 * 2)
+    check(v.value, p0)
+
+
+def test_gemm_c_abi_all_layouts(ad):
+    """Calls adb_gemm_f64 directly through ctypes with plain device pointers (the drop-in boundary)."""
+    import torch
+    from autodiff_b200 import _lib
+    rng = np.random.default_rng(1)
+    for (M, N, K, nb) in ((128, 128, 64, 1), (200, 136, 100, 1), (257, 129, 50, 3), (512, 384, 1030, 2)):
+        for a_kc in (True, False):
+            for b_kc in (True, False):
+                A = rng.standard_normal((nb, M, K)); B = rng.standard_normal((nb, K, N))
+                Ah = A if a_kc else np.ascontiguousarray(A.transpose(0, 2, 1))
+                Bh = np.ascontiguousarray(B.transpose(0, 2, 1)) if b_kc else B
+                At, Bt = torch.from_numpy(Ah).cuda(), torch.from_numpy(Bh).cuda()
+                Ct = torch.full((nb, M, N), float("nan"), dtype=torch.float64, device="cuda")
+                d = _lib.GemmDesc()
+                d.M, d.N, d.K, d.batch = M, N, K, nb
+                d.A, d.B, d.C = At.data_ptr(), Bt.data_ptr(), Ct.data_ptr()
+                d.a_sm, d.a_sk, d.a_sb = (K, 1, M * K) if a_kc else (1, M, M * K)
+                d.b_sk, d.b_sn, d.b_sb = (1, K, N * K) if b_kc else (N, 1, N * K)
+                d.c_sm, d.c_sn, d.c_sb = N, 1, M * N
+                aligned = (K % 2 == 0 if a_kc else M % 2 == 0) and (K % 2 == 0 if b_kc else N % 2 == 0)
+                for path in ((1, 2) if aligned else (0, 2)):
+                    Ct.fill_(float("nan"))
+                    _lib.check(_lib.lib().adb_gemm_f64_path(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream), path))
+                    torch.cuda.synchronize()
+                    check(Ct.cpu().numpy(), A @ B, what="gemm %s path %d" % ((M, N, K, nb, a_kc, b_kc), path))
+
+
+def test_large_gemm_properties(ad):
+    """BASELINE-size contraction checked through size-independent properties: linearity in A and a checksum
+    identity  ones^T (A B) ones == (ones^T A)(B ones)."""
+    rng = np.random.default_rng(6)
+    n = 2048
+    a = rng.standard_normal((n, n)); b = rng.standard_normal((n, n)); a2 = rng.standard_normal((n, n))
+    A, B, A2 = (ad.Variable(ad.to_device(v), name="v") for v in (a, b, a2))
+    c = ad.to_host((A @ B).eval_device())
+    c2 = ad.to_host((A2 @ B).eval_device())
+    csum = ad.to_host(((A + A2) @ B).eval_device())
+    check(csum, c + c2, tol=1e-12)
+    lhs = c.sum()
+    rhs = a.sum(0) @ b.sum(1)
+    assert abs(lhs - rhs) <= 1e-9 * abs(rhs) + 1e-6
+    check(c[:64], a[:64] @ b, tol=1e-12)

