@@ -10,6 +10,7 @@ from .. import _lib
 from ..device import DeviceArray, stream_ptr, to_device, torch
 from .node import Node, Variable
 
+kernel_timings = None   # bench.py sets this to a list; Einsum then records (description, start, stop) CUDA events
 _pending_flags = []   # (torch int32 tensor, exception) raised at the next host synchronisation
 
 

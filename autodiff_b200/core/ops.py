@@ -403,6 +403,14 @@ class Einsum(Node):
         tin = (_lib.Tensor * n)(*[a.tensor() for a in arrs])
         tout = out.tensor()
         spec = (",".join(subs) + "->" + out_sub).encode()
+        if engine.kernel_timings is not None:
+            t = torch()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(_lib.lib().adb_einsum(spec, n, tin, C.byref(tout), C.c_void_p(stream_ptr())))
+            e1.record()
+            engine.kernel_timings.append((spec.decode() + " " + "|".join(str(op.name) for op in self.operands), e0, e1))
+            return out
         _lib.check(_lib.lib().adb_einsum(spec, n, tin, C.byref(tout), C.c_void_p(stream_ptr())))
         return out
 

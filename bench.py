@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the autodiff_b200 hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--skip-e2e] [--skip-mlp]
+
+Metric (BASELINE.json): "einsum fwd+grad TFLOP/s (fp64)" on the einsum sweep (configs[1]):
+    C2a 'ij,jk->ik' 8192^2     C2b 'bij,bjk->bik' b=64 1024^2     C2c 'ijkl,jl->ik' A=(128,)*4
+each evaluated forward + ad.grad w.r.t. both operands (9 einsums per step, 3.712e12 flop).  One "step" is one
+pass over the sweep on synthetic N(0,1) fp64 inputs.  With --gpus N every rank runs the same sweep on its own
+GPU (the sweep has no exchange step: "replicas only") and `value` is the aggregate; the batch-
+sharded MLP training step WITH its NCCL gradient all-reduce (configs[0] and configs[2]) is reported in the same
+JSON line under "mlp_train".
+
+value  : inputs resident in HBM, results stay in HBM, CUDA-event timed.
+e2e    : the same sweep through the public API with host buffers: ad.Variable(pinned ndarray) ... node() ->
+         ndarray; host->device and device->host copies inside the timed region.
+--impl reference : the numpy oracle (oracle/np_autodiff.py, the reference's own algorithm: np.einsum without
+         BLAS, single thread) timed on the host cores on a bounded sample of the same sweep.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "einsum fwd+grad TFLOP/s (fp64)"
+FULL = {"C2a": ("ij,jk->ik", [(8192, 8192), (8192, 8192)]),
+        "C2b": ("bij,bjk->bik", [(64, 1024, 1024), (64, 1024, 1024)]),
+        "C2c": ("ijkl,jl->ik", [(128, 128, 128, 128), (128, 128)])}
+SAMPLE = {"C2a": ("ij,jk->ik", [(768, 768), (768, 768)]),
+          "C2b": ("bij,bjk->bik", [(8, 256, 256), (8, 256, 256)]),
+          "C2c": ("ijkl,jl->ik", [(48, 48, 48, 48), (48, 48)])}
+
+
+def einsum_flops(spec, shapes):
+    ext = {}
+    for sub, shp in zip(spec.split("->")[0].split(","), shapes):
+        for l, d in zip(sub, shp):
+            ext[l] = d
+    f = 2.0
+    for d in ext.values():
+        f *= d
+    return f
+
+
+def sweep_flops(cfg):
+    return sum(3 * einsum_flops(spec, shapes) for spec, shapes in cfg.values())   # fwd + 2 grads each
+
+
+def sweep_bytes(cfg):
+    """Algorithmic bytes of the HBM-bound member (C2c): 8*(|A|+|B|+|out|) per einsum, SURVEY.md 8d."""
+    spec, shapes = cfg["C2c"]
+    a = int(np.prod(shapes[0])); b = int(np.prod(shapes[1])); o = shapes[0][0] * shapes[0][2]
+    return 3 * 8 * (a + b + o)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (recipe in B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.stop = index, [], False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                r = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in r.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def build_sweep(ad, cfg, inputs):
+    """One step's graphs: E = Einsum(spec, A, B); dA, dB = ad.grad(E, [A, B]) for each member of the sweep."""
+    graphs = []
+    for name, (spec, _) in cfg.items():
+        a = ad.Variable(inputs[name][0], name=name + "_A")
+        b = ad.Variable(inputs[name][1], name=name + "_B")
+        e = ad.Einsum(spec, a, b)
+        da, db = ad.grad(e, [a, b])
+        graphs.append((name, e, da, db))
+    return graphs
+
+
+def run_gpu(args):
+    import torch
+    import autodiff_b200 as ad
+    from autodiff_b200.core import engine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ad.init(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = FULL
+    rng = np.random.default_rng(1337 + rank)
+    host_inputs = {}
+    for name, (spec, shapes) in cfg.items():
+        host_inputs[name] = []
+        for shp in shapes:
+            buf = ad.pinned_empty(shp)
+            rng.standard_normal(out=buf.reshape(-1))
+            host_inputs[name].append(buf)
+    dev_inputs = {n: [ad.to_device(v) for v in vs] for n, vs in host_inputs.items()}
+    flops = sweep_flops(cfg)
+
+    def step_resident(timers=None):
+        for name, e, da, db in build_sweep(ad, cfg, dev_inputs):
+            for node in (e, da, db):
+                node.eval_device()
+
+    def step_e2e():
+        outs = 0.0
+        for name, e, da, db in build_sweep(ad, cfg, host_inputs):
+            for node in (e, da, db):
+                h = node()
+                outs += float(h.reshape(-1)[0])
+        return outs
+
+    # ---- resident (kernel-path) number
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    engine.kernel_timings = []           # per-einsum CUDA-event pairs recorded by Einsum._eval_device
+    launches0 = ad.launch_count()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        barrier()
+    launches = ad.launch_count() - launches0
+    timings = engine.kernel_timings
+    engine.kernel_timings = None
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    value = world * flops / (ms * 1e-3) / 1e12
+
+    # ---- roofline of the dominant kernel: the 8192^3 DMMA GEMM launches of C2a (89% of the step's flops)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+    except Exception:
+        pass
+    gemm_ms = [a.elapsed_time(b) for (desc, a, b) in timings if "C2a" in desc]
+    gemm_flops = einsum_flops(*cfg["C2a"])
+    roof = None
+    if gemm_ms:
+        avg = sum(gemm_ms) / len(gemm_ms)
+        achieved = gemm_flops / (avg * 1e-3) / 1e12
+        peak = float(peaks.get("dmma_issue_peak_tflops", 37.03))
+        roof = {"bound": "tensor", "kernel": "gemm_tma_kernel (FP64 DMMA.8x8x4), C2a launches 2*8192^3 flop each",
+                "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "avg_launch_ms": round(avg, 4), "launches_timed": len(gemm_ms), "traffic": peaks.get("c2a_gemm_dram_bytes_per_launch"),
+                "peak_source": "measured DMMA.8x8x4 issue-rate peak on this pool's B200 (profiles/r01_probe_fp64_issue_rates.log); "
+                               "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM sustained measured 35.39"}
+    c2c_ms = [a.elapsed_time(b) for (desc, a, b) in timings if "C2c" in desc]
+    hbm = None
+    if c2c_ms:
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        pk = float(mp.get("hbm_gbs", 6650.0))
+        per_einsum = sweep_bytes(cfg) / 3
+        avg = sum(c2c_ms) / len(c2c_ms)
+        hbm = {"bound": "hbm", "kernel": "C2c einsums (reduce_kernel / ewise_kernel)", "achieved": round(per_einsum / (avg * 1e-3) / 1e9, 1),
+               "peak": pk, "unit": "GB/s", "frac": round(per_einsum / (avg * 1e-3) / 1e9 / pk, 4),
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6650 GB/s"}
+
+    # ---- end-to-end number (host buffers in, host arrays out)
+    e2e = None
+    if not args.skip_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        k = max(1, min(args.steps, 5))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        for _ in range(k):
+            step_e2e()
+        t1.record()
+        barrier()
+        wall = (time.perf_counter() - w0) * 1e3
+        ems = max_over_ranks(max(t0.elapsed_time(t1), wall)) / k
+        h2d = sum(int(np.prod(s)) * 8 for _, shapes in cfg.values() for s in shapes)
+        d2h = 0
+        for spec, shapes in cfg.values():
+            ext = {}
+            for sub, shp in zip(spec.split("->")[0].split(","), shapes):
+                ext.update(dict(zip(sub, shp)))
+            out_elems = int(np.prod([ext[l] for l in spec.split("->")[1]]))
+            d2h += 8 * (out_elems + int(np.prod(shapes[0])) + int(np.prod(shapes[1])))     # E, dA, dB
+        e2e = {"value": round(world * flops / (ems * 1e-3) / 1e12, 4), "unit": "TFLOP/s", "ms_per_step": round(ems, 3), "steps": k,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "ad.Variable(pinned ndarray) -> ad.Einsum / ad.grad -> node() returns host ndarray"}
+
+    mlp = None
+    if not args.skip_mlp:
+        try:
+            from autodiff_b200 import dp
+            mlp = dp.bench_mlp(args, dist)
+        except Exception as ex:      # reported, never silently dropped
+            mlp = {"error": repr(ex)[:300]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = run_reference_sample(reps=1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "impl": "autodiff_b200",
+                "config": {"workload": "einsum sweep fp64 (BASELINE configs[1]): 'ij,jk->ik' 8192^2 + 'bij,bjk->bik' b=64 1024^2 + "
+                                       "'ijkl,jl->ik' 128^4, each with ad.grad wrt both operands",
+                           "flop_per_step": flops, "l2": "inputs (512 MiB - 2 GiB each) exceed the 126 MB L2",
+                           "parallelism": "replicas x%d (the sweep has no exchange step)" % world},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches) * world,
+                "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "mlp_train": mlp}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def run_reference_sample(reps=1):
+    """The reference's algorithm (numpy oracle = np.einsum without BLAS, single thread) on a bounded sample."""
+    import oracle.np_autodiff as onp
+    rng = np.random.default_rng(1337)
+    inputs = {n: [rng.standard_normal(s) for s in shapes] for n, (spec, shapes) in SAMPLE.items()}
+    flops = sweep_flops(SAMPLE)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for name, e, da, db in build_sweep(onp, SAMPLE, inputs):
+            for node in (e, da, db):
+                node()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": round(flops / best / 1e12, 6), "unit": "TFLOP/s", "cores": 1, "host_cores_available": os.cpu_count(),
+            "kind": "port", "seconds": round(best, 3),
+            "sample": "same sweep scaled to 'ij,jk->ik' 768^2, 'bij,bjk->bik' b=8 256^2, 'ijkl,jl->ik' 48^4, fwd + 2 grads each "
+                      "(%.3g flop); np.einsum without optimize is single-threaded C (reference ops.py:180)" % flops}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        run_reference_sample()
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = run_reference_sample()
+    dt = (time.perf_counter() - t0) / args.steps
+    flops = sweep_flops(SAMPLE)
+    v = round(flops / dt / 1e12, 6)
+    last["value"] = v
+    line = {"metric": METRIC, "value": v, "unit": "TFLOP/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "einsum sweep fp64 (BASELINE configs[1]), bounded sample per step: " + last["sample"]},
+            "cpu_baseline": last, "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="autodiff_b200")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-mlp", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,12 +38,26 @@ def check(x, ref, tol=TOL, what=""):
     assert e <= tol, "%s rel err %.3e > %.1e" % (what, e, tol)
 
 
+# Outputs that are ZERO BY MATHEMATICS (the gradient of sum(softmax(x)) == const, and derivatives of it): the
+# reference's value there is pure rounding noise (~1e-14), so "relative to max|ref|" has no meaning.  They are
+# held to the same 1e-12 but relative to the magnitude of the case's forward value instead.
+ZERO_BY_MATH = {"softmax_2d/d1_0", "softmax_2d/d2_0", "softmax_1d/d1_0", "softmax_1d/d2_0", "softmax_4d/d1_0", "softmax_4d/d2_0",
+                "softmax_ce/d2_0"}
+
+
 @pytest.mark.parametrize("name", sorted(cases.CASES))
 def test_case_against_reference_golden(name, ad):
     gold = np.load(os.path.join(GOLD, "cases.npz"))
     nodes = cases.derive(ad, name)
     for key, node in nodes.items():
-        check(node(), gold[name + "/" + key], what=name + "/" + key)
+        ref = gold[name + "/" + key]
+        if name + "/" + key in ZERO_BY_MATH:
+            fscale = float(np.max(np.abs(gold[name + "/f"])))
+            assert np.max(np.abs(ref)) < 1e-12 * fscale                      # the reference itself is at noise level
+            got = np.broadcast_to(np.asarray(node()), ref.shape)
+            assert np.max(np.abs(got - ref)) <= TOL * fscale, name + "/" + key
+        else:
+            check(node(), ref, what=name + "/" + key)
 
 
 def test_readme_numbers(ad):
