@@ -25,6 +25,13 @@ def _has_value(node):
     return node._dev is not None or node._host is not None
 
 
+def scalar_of(node):
+    """Host-known 0-d constant of a leaf, else None."""
+    if isinstance(node, Variable):
+        return node.host_scalar()
+    return None
+
+
 def evaluate(top):
     stack = [top]
     while stack:
@@ -37,7 +44,7 @@ def evaluate(top):
             node._host = node._eval()
             stack.pop()
             continue
-        pending = [c for c in node.children if not _has_value(c)]
+        pending = [c for c in node.children if not _has_value(c) and scalar_of(c) is None]
         if pending:
             stack.extend(reversed(pending))
             continue
@@ -55,13 +62,6 @@ def dev(node):
             if node._dev is None:
                 node._dev = to_device(np.asarray(node._host))
     return node._dev
-
-
-def scalar_of(node):
-    """Host-known 0-d constant of a leaf, else None."""
-    if isinstance(node, Variable):
-        return node.host_scalar()
-    return None
 
 
 def add_pending_flag(flag_tensor, exc):

@@ -31,6 +31,7 @@ class Node:
         self.name = name
         self._host = None
         self._dev = None
+        self._dev_override = False
         self.shape = None
         self.context_list = Node.context_list.copy()
         self.id = Node.id
@@ -47,8 +48,10 @@ class Node:
     def cached(self, value):
         if isinstance(value, DeviceArray):
             self._dev, self._host = value, None
+            self._dev_override = True       # the device value no longer mirrors a host-known leaf value
         else:
             self._host, self._dev = value, None
+            self._dev_override = False
 
     def _download(self, dev):
         host = to_host(dev)
@@ -195,10 +198,14 @@ class Variable(Node):
         self.cached = val
 
     def host_scalar(self):
-        """Python float when this leaf is a host-known 0-d constant (folded into kernels as an immediate)."""
-        if self._dev is not None and self._host is None:
+        """Python float when this leaf is a host-known 0-d constant (folded into kernels as an immediate).
+        An uploaded copy in `_dev` does not hide the host value; only an explicit `cached = DeviceArray` does."""
+        if self._host is not None:
+            v = self._host
+        elif self._dev_override:
             return None
-        v = self._host if self._host is not None else self._value
+        else:
+            v = self._value
         if isinstance(v, DeviceArray):
             return None
         if isinstance(v, numbers.Number):
@@ -273,8 +280,8 @@ class ConstFill(Variable):
         Node.cached.fset(self, value)
 
     def host_scalar(self):
-        if self.fill is not None and self._fill_shape == () and self._host is None:
-            return self.fill
+        if self.fill is not None and self._host is None:
+            return self.fill if self._fill_shape == () else None     # never materialise just to look
         return Variable.host_scalar(self)
 
     def _eval(self):

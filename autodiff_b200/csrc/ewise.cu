@@ -22,9 +22,29 @@ constexpr int EW_RANK = 5;
 constexpr int EW_V = 4;
 constexpr int EW_TEMPS = 8;
 
+// q = n / d for n < 2^31 without a divide: d == 1 ? n : umulhi(n, mul) >> shr   (round-up magic number)
+struct FastDiv {
+    unsigned mul, shr, d, _pad;
+};
+static FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d; f._pad = 0;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+    unsigned lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const unsigned p = 31 + lg;
+    f.mul = (unsigned)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+    return f;
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+
 struct EwParams {
-    int n_in, n_out, n_instr, _pad;
+    int n_in, n_out, n_instr, nd;
     long long dim[EW_RANK];  // dim[0] innermost (collapsed iteration space of the outputs)
+    FastDiv div_chunks0;     // divisor ceil(dim[0]/4)
+    FastDiv div_dim[EW_RANK];
+    unsigned long long total;  // work items = chunks0 * prod(dim[1..])
     long long in_stride[ADB_EW_MAX_IN][EW_RANK];
     long long out_stride[ADB_EW_MAX_OUT][EW_RANK];
     const double* in[ADB_EW_MAX_IN];
@@ -71,22 +91,38 @@ __device__ __forceinline__ void store_out(const EwParams& P, int j, long long ba
 
 #define EW_FOR for (int e = 0; e < EW_V; ++e)
 
-template <int NT>
-__global__ void __launch_bounds__(256, NT <= 2 ? 3 : 1) ewise_kernel(const __grid_constant__ EwParams P) {
-    const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
-    const long long total = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += step) {
+__device__ __noinline__ double ew_pow(double a, double b) { return pow(a, b); }   // keeps pow's registers out of the main loop
+
+template <int NT, bool BIG>
+__global__ void __launch_bounds__(256, NT <= 2 ? 3 : 2) ewise_kernel(const __grid_constant__ EwParams P) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < P.total; w += step) {
         long long idx[EW_RANK];
-        long long o = w / chunks0;
-        idx[0] = (w - o * chunks0) * EW_V;
+        if (BIG) {      // >= 2^31 work items: plain 64-bit divisions
+            const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
+            long long o = (long long)w / chunks0;
+            idx[0] = ((long long)w - o * chunks0) * EW_V;
 #pragma unroll
-        for (int k = 1; k < EW_RANK; ++k) {
-            const long long d = P.dim[k];
-            if (d == 1) { idx[k] = 0; continue; }
-            const long long qn = o / d;
-            idx[k] = o - qn * d;
-            o = qn;
+            for (int k = 1; k < EW_RANK; ++k) {
+                const long long d = P.dim[k];
+                const long long qn = o / d;
+                idx[k] = o - qn * d;
+                o = qn;
+            }
+        } else {
+            const unsigned w32 = (unsigned)w;
+            unsigned o = fastdiv(w32, P.div_chunks0);
+            idx[0] = (long long)(w32 - o * P.div_chunks0.d) * EW_V;
+#pragma unroll
+            for (int k = 1; k < EW_RANK; ++k) {
+                if (k < P.nd) {
+                    const unsigned qn = fastdiv(o, P.div_dim[k]);
+                    idx[k] = o - qn * P.div_dim[k].d;
+                    o = qn;
+                } else {
+                    idx[k] = 0;
+                }
+            }
         }
         const long long rem = P.dim[0] - idx[0];
         const int nvalid = rem >= EW_V ? EW_V : (int)rem;
@@ -100,6 +136,7 @@ __global__ void __launch_bounds__(256, NT <= 2 ? 3 : 1) ewise_kernel(const __gri
 #pragma unroll
             for (int e = 0; e < EW_V; ++e) t[k].v[e] = 0.0;
 
+#pragma unroll 1
         for (int pc = 0; pc < P.n_instr; ++pc) {
             const int op = P.code[pc].op;
             const int arg = P.code[pc].arg;
@@ -139,11 +176,11 @@ __global__ void __launch_bounds__(256, NT <= 2 ? 3 : 1) ewise_kernel(const __gri
                     break;
                 case ADB_EW_POW >> 2:
 #pragma unroll
-                    EW_FOR acc.v[e] = pow(acc.v[e], x.v[e]);
+                    EW_FOR acc.v[e] = ew_pow(acc.v[e], x.v[e]);
                     break;
                 case ADB_EW_RPOW >> 2:
 #pragma unroll
-                    EW_FOR acc.v[e] = pow(x.v[e], acc.v[e]);
+                    EW_FOR acc.v[e] = ew_pow(x.v[e], acc.v[e]);
                     break;
                 case ADB_EW_MAX >> 2:
 #pragma unroll
@@ -268,7 +305,7 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
 
     // collapse, walking from the innermost dim outwards
     EwParams P;
-    P.n_in = n_in; P.n_out = n_out; P.n_instr = n_instr; P._pad = 0;
+    P.n_in = n_in; P.n_out = n_out; P.n_instr = n_instr; P.nd = 1;
     int nd = 0;
     for (int k = rank - 1; k >= 0; --k) {
         if (shape[k] == 1) continue;
@@ -310,14 +347,27 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
 
     const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
     const long long work = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
+    P.nd = nd < 1 ? 1 : nd;
+    P.total = (unsigned long long)work;
+    bool big = work >= (1LL << 31);
+    for (int k = 0; k < EW_RANK; ++k) big = big || P.dim[k] >= (1LL << 31);
+    if (!big) {
+        P.div_chunks0 = make_fastdiv((unsigned)chunks0);
+        for (int k = 0; k < EW_RANK; ++k) P.div_dim[k] = make_fastdiv((unsigned)P.dim[k]);
+    }
     long long blocks = (work + 255) / 256;
     const long long cap = (long long)sm_count() * 8;   // 8 resident 256-thread CTAs per SM, grid-stride beyond
     if (blocks > cap) blocks = cap;
     int max_temp = -1;
     for (int i = 0; i < n_instr; ++i)
         if ((code[i].op & 3) == 3 || (code[i].op >> 2) == (ADB_EW_STORE_T >> 2)) max_temp = code[i].arg > max_temp ? code[i].arg : max_temp;
-    if (max_temp < 2) ewise_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(P);
-    else ewise_kernel<EW_TEMPS><<<(unsigned)blocks, 256, 0, st>>>(P);
+    if (max_temp < 2) {
+        if (big) ewise_kernel<2, true><<<(unsigned)blocks, 256, 0, st>>>(P);
+        else ewise_kernel<2, false><<<(unsigned)blocks, 256, 0, st>>>(P);
+    } else {
+        if (big) ewise_kernel<EW_TEMPS, true><<<(unsigned)blocks, 256, 0, st>>>(P);
+        else ewise_kernel<EW_TEMPS, false><<<(unsigned)blocks, 256, 0, st>>>(P);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("ewise launch failed: %s", cudaGetErrorString(e));
     count_launch();

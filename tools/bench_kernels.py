@@ -1,0 +1,102 @@
+"""Per-kernel achieved bandwidth / throughput on one B200 (CUDA events, inputs > L2, 3 warm-ups, best of 5).
+Algorithmic bytes = 8 * (distinct input elements + output elements), SURVEY.md 8d.  Writes gpurun_out/kernels.json."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import autodiff_b200 as ad
+
+ad.init(0)
+PEAK = 6555.8
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+rng = np.random.default_rng(0)
+results = []
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
+def dev(shape, positive=False):
+    a = rng.random(shape) + 0.5 if positive else rng.standard_normal(shape)
+    return ad.to_device(a)
+
+
+def timeit(name, build, nbytes, flops=None, reps=5):
+    if only and only not in name:
+        return
+    for _ in range(3):
+        build().eval_device()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        node = build()
+        l0 = ad.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        node.eval_device()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+        launches = ad.launch_count() - l0
+    gbs = nbytes / (best * 1e-3) / 1e9
+    row = {"name": name, "ms": round(best, 4), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 3), "launches": launches}
+    if flops:
+        row["TFLOP/s"] = round(flops / (best * 1e-3) / 1e12, 2)
+    results.append(row)
+    print(row, flush=True)
+
+
+R, Cc = 8192, 4096
+n = R * Cc
+x = dev((R, Cc)); y = dev((R, Cc), positive=True); b = dev((Cc,)); xo = dev((R, Cc + 1))
+V = lambda d, name="v": ad.Variable(d, name=name)
+timeit("copy (Concat column block) 8192x4096", lambda: ad.Concat(V(x), ad.ConstFill((R, 1), 1.0), axis=1), 8 * (2 * n + R))
+timeit("add x+y", lambda: V(x) + V(y), 8 * 3 * n)
+timeit("mul x*y*b", lambda: V(x) * V(y) * V(b), 8 * (3 * n + Cc))
+timeit("relu", lambda: ad.ReLU(V(x)), 8 * 2 * n)
+timeit("recipr", lambda: ad.Recipr(V(y)), 8 * 2 * n)
+timeit("exp", lambda: ad.Exp(V(x)), 8 * 2 * n)
+timeit("sigmoid", lambda: ad.Sigmoid(V(x)), 8 * 2 * n)
+timeit("log", lambda: ad.Log(V(y)), 8 * 2 * n)
+timeit("tanh macro (7 nodes)", lambda: ad.Tanh(V(x)), 8 * 2 * n)
+timeit("relu grad prev*self*Recipr(self)", lambda: (lambda r: V(y) * r * ad.Recipr(r))(V(x)), 8 * 3 * n)
+timeit("pitched relu 8192x4097", lambda: ad.ReLU(V(xo)), 8 * 2 * R * (Cc + 1))
+timeit("sum rows ab->a", lambda: ad.Einsum("ab->a", V(x)), 8 * (n + R))
+timeit("sum cols ab->b", lambda: ad.Einsum("ab->b", V(x)), 8 * (n + Cc))
+timeit("sum all ab->", lambda: ad.Einsum("ab->", V(x)), 8 * n)
+timeit("softmax denominator bi,o->bo", lambda: ad.Einsum("bi,o->bo", V(x), np.array([1])), 8 * (n + R))
+timeit("frobenius", lambda: ad.FrobeniusNorm(V(x)), 8 * n)
+lab = np.zeros((R, Cc)); lab[np.arange(R), rng.integers(0, Cc, R)] = 1.0
+labd = ad.to_device(lab)
+timeit("softmax_ce 8192x4096", lambda: ad.SoftmaxCEWithLogits(labels=V(labd), logits=V(x)), 8 * (2 * n + R))
+p, g, m, v = dev((4097, 4096)), dev((4097, 4096)), dev((4097, 4096)), dev((4097, 4096), positive=True)
+
+
+class _AdamNode:
+    def __init__(self):
+        self.opt = ad.Adam(1, lr=1e-3); self.opt.m[0] = m; self.opt.v[0] = v; self.opt.step = 3
+
+    def eval_device(self):
+        return self.opt([p], [g])[0]
+
+
+timeit("adam update 4097x4096 (4 in, 3 out)", lambda: _AdamNode(), 8 * 7 * 4097 * 4096)
+del x, y, xo, labd, p, g, m, v
+S = 128
+A4 = dev((S, S, S, S)); B2 = dev((S, S)); G2 = dev((S, S))
+nb = 8 * (S ** 4 + 2 * S * S)
+timeit("C2c fwd ijkl,jl->ik", lambda: ad.Einsum("ijkl,jl->ik", V(A4), V(B2)), nb)
+timeit("C2c dB ijkl,ik->jl", lambda: ad.Einsum("ijkl,ik->jl", V(A4), V(G2)), nb)
+timeit("C2c dA ik,jl->ijkl", lambda: ad.Einsum("ik,jl->ijkl", V(G2), V(B2)), nb)
+del A4
+for (M, N, K, tag) in ((8192, 8192, 8192, "C2a"), (8192, 4096, 4097, "C3 fwd"), (1024, 4096, 4097, "C3 fwd b/8"), (512, 1024, 1024, "C5 h@w")):
+    a, bb = dev((M, K)), dev((K, N))
+    timeit("gemm %s %dx%dx%d" % (tag, M, N, K), lambda: V(a) @ V(bb), 8 * (M * K + K * N + M * N), flops=2.0 * M * N * K, reps=3)
+    del a, bb
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(results, open("gpurun_out/kernels.json", "w"), indent=1)
