@@ -10,6 +10,7 @@ from .. import _lib
 from ..device import DeviceArray, stream_ptr, to_device, torch
 from .node import Node, Variable
 
+fusion_enabled = True   # set False to run one kernel per node (debugging / A-B measurements)
 kernel_timings = None   # bench.py sets this to a list; Einsum then records (description, start, stop) CUDA events
 _pending_flags = []   # (torch int32 tensor, exception) raised at the next host synchronisation
 
@@ -32,7 +33,83 @@ def scalar_of(node):
     return None
 
 
-def evaluate(top):
+class _Plan:
+    __slots__ = ("groups", "absorbed")
+
+    def __init__(self):
+        self.groups = {}      # id(root) -> {id(member): member}
+        self.absorbed = {}    # id(member) -> root
+
+
+def _plan(tops):
+    """Finds the not-yet-evaluated sub-DAG under `tops`, counts consumers and forms elementwise fusion groups."""
+    from . import fusion
+    plan = _Plan()
+    top_ids = {id(t) for t in tops}
+    order, consumers, seen = [], {}, set()
+    stack = [(t, False) for t in reversed(tops)]
+    while stack:
+        node, done = stack.pop()
+        if done:
+            order.append(node)
+            continue
+        if id(node) in seen or _has_value(node):
+            continue
+        seen.add(id(node))
+        stack.append((node, True))
+        if not _is_device_node(node):
+            continue          # opaque user op: pulls its own inputs through child()
+        for c in node.children:
+            if _has_value(c) or scalar_of(c) is not None:
+                continue
+            consumers.setdefault(id(c), []).append(node)
+            if id(c) not in seen:
+                stack.append((c, False))
+    if not fusion_enabled:
+        return plan
+    for node in reversed(order):          # consumers before producers
+        if id(node) in plan.absorbed or fusion.ew_spec(node) is None:
+            continue
+        shape = fusion.norm_shape(node.shape)
+        if shape is None:
+            continue
+        members = {id(node): node}
+        frontier, deferred = list(node.children), []
+        while frontier:
+            x = frontier.pop()
+            k = id(x)
+            if k in members or k in plan.absorbed or k in top_ids or k not in consumers:
+                continue
+            if _has_value(x) or fusion.ew_spec(x) is None or fusion.norm_shape(x.shape) != shape:
+                continue
+            if len(members) >= fusion.MAX_MEMBERS:
+                continue
+            if not all(id(c) in members for c in consumers[k]):
+                deferred.append(x)
+                continue
+            members[k] = x
+            frontier.extend(x.children)
+            frontier.extend(deferred)
+            deferred = []
+        if len(members) > 1:
+            plan.groups[id(node)] = members
+            for k, m in members.items():
+                if m is not node:
+                    plan.absorbed[k] = node
+    return plan
+
+
+def _group_inputs(members):
+    deps = []
+    for m in members.values():
+        for c in m.children:
+            if id(c) not in members and not _has_value(c) and scalar_of(c) is None:
+                deps.append(c)
+    return deps
+
+
+def _execute(top, plan):
+    from . import fusion
     stack = [top]
     while stack:
         node = stack[-1]
@@ -44,12 +121,40 @@ def evaluate(top):
             node._host = node._eval()
             stack.pop()
             continue
-        pending = [c for c in node.children if not _has_value(c) and scalar_of(c) is None]
+        members = plan.groups.get(id(node))
+        if members is not None:
+            pending = _group_inputs(members)
+        else:
+            pending = [c for c in node.children if not _has_value(c) and scalar_of(c) is None]
         if pending:
             stack.extend(reversed(pending))
             continue
-        node._dev = node._eval_device()
+        if members is not None:
+            try:
+                node._dev = fusion.run_group(node, members, dev, scalar_of, run_program)
+            except fusion.FusionOverflow:
+                del plan.groups[id(node)]          # does not fit one program: evaluate the members one by one
+                for k in members:
+                    plan.absorbed.pop(k, None)
+                continue
+        else:
+            node._dev = node._eval_device()
         stack.pop()
+
+
+def evaluate_many(tops, on_ready=None):
+    """Evaluates several graph outputs with one fusion plan (consumer counts span all of them).
+    `on_ready(node)` fires as soon as each output's kernels are queued (used to overlap all-reduces)."""
+    tops = list(tops)
+    plan = _plan([t for t in tops if not _has_value(t)])
+    for t in tops:
+        _execute(t, plan)
+        if on_ready is not None:
+            on_ready(t)
+
+
+def evaluate(top):
+    evaluate_many([top])
 
 
 def dev(node):

@@ -62,44 +62,32 @@ def ReduceSumToShape(tensor, to_shape):
 
 
 # ------------------------------------------------------------------------------------------------ n-ary
-def _nary_device(node, kind, identity):
-    """Left-to-right fold `((id op c0) op c1) ...` as ONE kernel; host-known 0-d leaves become immediates and
-    exact identities (x+0, x*1) are dropped."""
+def _single(node):
+    """Evaluates one fusable node on its own through the same emitter the fusion groups use."""
+    from . import fusion
+    try:
+        return fusion.run_group(node, {id(node): node}, dev, scalar_of, run_program)
+    except fusion.FusionOverflow:
+        spec = node._ew_spec()
+        if spec[0] != "nary":
+            raise
+        return _nary_chunked(node, spec[1], spec[2])
+
+
+def _nary_chunked(node, kind, identity):
+    """n-ary fold with more operands than one program can take: left-to-right in chunks (same association)."""
     terms, shapes = [], []
     for ch in node.children:
         s = scalar_of(ch)
         if s is not None:
-            if s == identity:
-                continue
-            terms.append((IMM, s))
-        elif isinstance(ch, ConstFill) and ch.fill == identity and ch._host is None:
-            shapes.append(tuple(ch.shape))      # a block of ones/zeros only contributes its shape
+            if s != identity:
+                terms.append((IMM, s))
         else:
             a = dev(ch)
             terms.append((IN, a))
             shapes.append(a.shape)
     out_shape = tuple(np.broadcast_shapes(*shapes)) if shapes else ()
-    if not terms:
-        terms = [(IMM, float(identity))]
-    if len(terms) == 1 and terms[0][0] == IN and terms[0][1].shape == tuple(out_shape):
-        return terms[0][1]
-    code, inputs = [], []
-    for i, (src, val) in enumerate(terms):
-        op = _lib.EW_LOAD if i == 0 else kind
-        if src == IN:
-            code.append((op | IN, len(inputs), 0.0))
-            inputs.append(val)
-        else:
-            code.append((op | IMM, 0, val))
-    code.append((_lib.EW_STORE_OUT, 0, 0.0))
-    if len(inputs) > _lib.EW_MAX_IN or len(code) > _lib.EW_MAX_INSTR:
-        return _nary_chunked(terms, kind, out_shape)
-    return run_program(code, inputs, out_shape)
-
-
-def _nary_chunked(terms, kind, out_shape):
-    acc = None
-    i = 0
+    acc, i = None, 0
     while i < len(terms):
         code, inputs = [], []
         if acc is not None:
@@ -115,7 +103,7 @@ def _nary_chunked(terms, kind, out_shape):
                 code.append((op | IMM, 0, val))
             i += 1
         code.append((_lib.EW_STORE_OUT, 0, 0.0))
-        shape = out_shape if i == len(terms) else np.broadcast_shapes(*[t.shape for t in inputs])
+        shape = out_shape if i == len(terms) else tuple(np.broadcast_shapes(*[t.shape for t in inputs]))
         acc = run_program(code, inputs, shape)
     return acc
 
@@ -129,8 +117,11 @@ class Add(Node):
         super().__init__(list(elems), name)
         self.shape = shape_from_elems(*self.children)
 
+    def _ew_spec(self):
+        return ("nary", _lib.EW_ADD, 0.0)
+
     def _eval_device(self):
-        return _nary_device(self, _lib.EW_ADD, 0.0)
+        return _single(self)
 
     def _partial_derivative(self, wrt, previous_grad):
         wrt_count = self.children.count(wrt)
@@ -145,8 +136,11 @@ class Mul(Node):
         super().__init__(list(elems), name)
         self.shape = shape_from_elems(*self.children)
 
+    def _ew_spec(self):
+        return ("nary", _lib.EW_MUL, 1.0)
+
     def _eval_device(self):
-        return _nary_device(self, _lib.EW_MUL, 1.0)
+        return _single(self)
 
     def _partial_derivative(self, wrt, previous_grad):
         add_list = []
@@ -171,14 +165,11 @@ class _Elementwise(Node):
     def _code(self):
         return list(self.program)
 
+    def _ew_spec(self):
+        return ("unary", self._code())
+
     def _eval_device(self):
-        s = scalar_of(self.node)
-        if s is not None:
-            code = [(_lib.EW_LOAD | IMM, 0, s)] + self._code() + [(_lib.EW_STORE_OUT, 0, 0.0)]
-            return run_program(code, [], ())
-        x = dev(self.node)
-        code = [(_lib.EW_LOAD | IN, 0, 0.0)] + self._code() + [(_lib.EW_STORE_OUT, 0, 0.0)]
-        return run_program(code, [x], x.shape)
+        return _single(self)
 
     def _partial_derivative(self, wrt, previous_grad):
         if self.node == wrt:
@@ -226,8 +217,8 @@ class Log(_Elementwise):
 class Identity(_Elementwise):
     default_name = "Identity"
 
-    def _eval_device(self):
-        return dev(self.node)          # the reference returns the child's array itself (ops.py:324)
+    def _ew_spec(self):
+        return ("alias",)              # the reference returns the child's array itself (ops.py:324)
 
     def _pd(self, previous_grad):
         return previous_grad
@@ -281,19 +272,11 @@ class Pow(Node):
         self.second = self.children[1]
         self.shape = shape_from_elems(*self.children)
 
+    def _ew_spec(self):
+        return ("pow",)
+
     def _eval_device(self):
-        code, inputs = [], []
-        for i, ch in enumerate(self.children):
-            op = _lib.EW_LOAD if i == 0 else _lib.EW_POW
-            s = scalar_of(ch)
-            if s is not None:
-                code.append((op | IMM, 0, s))
-            else:
-                code.append((op | IN, len(inputs), 0.0))
-                inputs.append(dev(ch))
-        code.append((_lib.EW_STORE_OUT, 0, 0.0))
-        shape = np.broadcast_shapes(*[t.shape for t in inputs]) if inputs else ()
-        return run_program(code, inputs, shape)
+        return _single(self)
 
     def _partial_derivative(self, wrt, previous_grad):
         if self.first == self.second == wrt:
@@ -351,6 +334,14 @@ class Einsum(Node):
     @staticmethod
     def split_dots(op_str):
         return re.findall(r"\.{3}|\S", op_str)
+
+    def _ew_spec(self):
+        """'ab->ab' (inserted by ReduceSumToShape, ops.py:31-39) is a pass-through for fusion."""
+        a = self.opnames[0]
+        if len(self.operands) == 1 and a == self.opnames[-1] and "." not in a and len(set(a)) == len(a) \
+                and len(a) == len(self.operands[0].shape):
+            return ("alias",)
+        return None
 
     # ---- device evaluation
     def _eval_device(self):

@@ -19,7 +19,6 @@
 namespace adb {
 
 constexpr int EW_RANK = 5;
-constexpr int EW_V = 4;
 constexpr int EW_TEMPS = 8;
 
 // q = n / d for n < 2^31 without a divide: d == 1 ? n : umulhi(n, mul) >> shr   (round-up magic number)
@@ -53,55 +52,62 @@ struct EwParams {
     adb_ew_instr code[ADB_EW_MAX_INSTR];
 };
 
-struct V4 {
-    double v[EW_V];
+template <int V>
+struct Vec {
+    double v[V];
 };
 
-__device__ __forceinline__ V4 load_in(const EwParams& P, int i, long long base, int nvalid) {
-    V4 r;
+template <int V>
+__device__ __forceinline__ Vec<V> load_in(const EwParams& P, int i, long long base, int nvalid) {
+    Vec<V> r;
     const double* p = P.in[i] + base;
     const long long s0 = P.in_stride[i][0];
     if (s0 == 0) {
         const double x = __ldg(p);
 #pragma unroll
-        for (int e = 0; e < EW_V; ++e) r.v[e] = x;
-    } else if (((P.in_vec >> i) & 1u) && nvalid == EW_V) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-        const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+        for (int e = 0; e < V; ++e) r.v[e] = x;
+    } else if (((P.in_vec >> i) & 1u) && nvalid == V) {
+#pragma unroll
+        for (int e = 0; e < V / 2; ++e) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(p) + e);
+            r.v[2 * e] = a.x;
+            r.v[2 * e + 1] = a.y;
+        }
     } else {
 #pragma unroll
-        for (int e = 0; e < EW_V; ++e) r.v[e] = (e < nvalid) ? __ldg(p + e * s0) : 0.0;
+        for (int e = 0; e < V; ++e) r.v[e] = (e < nvalid) ? __ldg(p + e * s0) : 0.0;
     }
     return r;
 }
 
-__device__ __forceinline__ void store_out(const EwParams& P, int j, long long base, int nvalid, const V4& a) {
+template <int V>
+__device__ __forceinline__ void store_out(const EwParams& P, int j, long long base, int nvalid, const Vec<V>& a) {
     double* p = P.out[j] + base;
     const long long s0 = P.out_stride[j][0];
-    if (((P.out_vec >> j) & 1u) && nvalid == EW_V) {
-        reinterpret_cast<double2*>(p)[0] = make_double2(a.v[0], a.v[1]);
-        reinterpret_cast<double2*>(p)[1] = make_double2(a.v[2], a.v[3]);
+    if (((P.out_vec >> j) & 1u) && nvalid == V) {
+#pragma unroll
+        for (int e = 0; e < V / 2; ++e) __stcs(reinterpret_cast<double2*>(p) + e, make_double2(a.v[2 * e], a.v[2 * e + 1]));
     } else {
 #pragma unroll
-        for (int e = 0; e < EW_V; ++e)
+        for (int e = 0; e < V; ++e)
             if (e < nvalid) p[e * s0] = a.v[e];
     }
 }
 
-#define EW_FOR for (int e = 0; e < EW_V; ++e)
+#define EW_FOR for (int e = 0; e < V; ++e)
 
 __device__ __noinline__ double ew_pow(double a, double b) { return pow(a, b); }   // keeps pow's registers out of the main loop
 
-template <int NT, bool BIG>
-__global__ void __launch_bounds__(256, NT <= 2 ? 3 : 2) ewise_kernel(const __grid_constant__ EwParams P) {
+// V elements per thread per step (V = 8: four 128-bit loads in flight per operand), NT register temps.
+template <int V, int NT, bool BIG>
+__global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel(const __grid_constant__ EwParams P) {
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < P.total; w += step) {
         long long idx[EW_RANK];
         if (BIG) {      // >= 2^31 work items: plain 64-bit divisions
-            const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
+            const long long chunks0 = (P.dim[0] + V - 1) / V;
             long long o = (long long)w / chunks0;
-            idx[0] = ((long long)w - o * chunks0) * EW_V;
+            idx[0] = ((long long)w - o * chunks0) * V;
 #pragma unroll
             for (int k = 1; k < EW_RANK; ++k) {
                 const long long d = P.dim[k];
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(256, NT <= 2 ? 3 : 2) ewise_kernel(const __gri
         } else {
             const unsigned w32 = (unsigned)w;
             unsigned o = fastdiv(w32, P.div_chunks0);
-            idx[0] = (long long)(w32 - o * P.div_chunks0.d) * EW_V;
+            idx[0] = (long long)(w32 - o * P.div_chunks0.d) * V;
 #pragma unroll
             for (int k = 1; k < EW_RANK; ++k) {
                 if (k < P.nd) {
@@ -125,34 +131,31 @@ __global__ void __launch_bounds__(256, NT <= 2 ? 3 : 2) ewise_kernel(const __gri
             }
         }
         const long long rem = P.dim[0] - idx[0];
-        const int nvalid = rem >= EW_V ? EW_V : (int)rem;
+        const int nvalid = rem >= V ? V : (int)rem;
 
-        V4 acc;
-        V4 t[NT];
+        Vec<V> acc;
+        Vec<V> t[NT > 0 ? NT : 1];
 #pragma unroll
-        for (int e = 0; e < EW_V; ++e) acc.v[e] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NT; ++k)
-#pragma unroll
-            for (int e = 0; e < EW_V; ++e) t[k].v[e] = 0.0;
+        for (int e = 0; e < V; ++e) acc.v[e] = 0.0;
 
 #pragma unroll 1
-        for (int pc = 0; pc < P.n_instr; ++pc) {
+        for (int pc = 0; pc < P.n_instr; ++pc) {  // interpreter loop (kept rolled)
             const int op = P.code[pc].op;
             const int arg = P.code[pc].arg;
             const double imm = P.code[pc].imm;
-            V4 x;  // second operand for binary ops
+            Vec<V> x;  // second operand for binary ops
             const int src = op & 3;  // 0 = none/unary, 1 = input tensor, 2 = immediate, 3 = temp
             if (src == 1) {
                 long long base = 0;
 #pragma unroll
-                for (int k = 0; k < EW_RANK; ++k) base += idx[k] * P.in_stride[arg][k];
-                x = load_in(P, arg, base, nvalid);
+                for (int k = 0; k < EW_RANK; ++k)
+                    if (k < P.nd) base += idx[k] * P.in_stride[arg][k];
+                x = load_in<V>(P, arg, base, nvalid);
             } else if (src == 2) {
 #pragma unroll
                 EW_FOR x.v[e] = imm;
             } else if (src == 3) {
-                // temps live in registers: select by a uniform switch, never by dynamic indexing
+                // temps live in registers: selected by uniform compares, never by dynamic indexing
 #pragma unroll
                 for (int k = 0; k < NT; ++k)
                     if (arg == k) x = t[k];
@@ -194,8 +197,9 @@ __global__ void __launch_bounds__(256, NT <= 2 ? 3 : 2) ewise_kernel(const __gri
                 case ADB_EW_STORE_OUT >> 2: {
                     long long base = 0;
 #pragma unroll
-                    for (int k = 0; k < EW_RANK; ++k) base += idx[k] * P.out_stride[arg][k];
-                    store_out(P, arg, base, nvalid, acc);
+                    for (int k = 0; k < EW_RANK; ++k)
+                        if (k < P.nd) base += idx[k] * P.out_stride[arg][k];
+                    store_out<V>(P, arg, base, nvalid, acc);
                     break;
                 }
                 case ADB_EW_NEG >> 2:
@@ -345,7 +349,11 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
     }
     for (int i = 0; i < n_instr; ++i) P.code[i] = code[i];
 
-    const long long chunks0 = (P.dim[0] + EW_V - 1) / EW_V;
+    int max_temp = -1;
+    for (int i = 0; i < n_instr; ++i)
+        if ((code[i].op & 3) == 3 || (code[i].op >> 2) == (ADB_EW_STORE_T >> 2)) max_temp = code[i].arg > max_temp ? code[i].arg : max_temp;
+    const int V = max_temp < 2 ? 8 : 4;
+    const long long chunks0 = (P.dim[0] + V - 1) / V;
     const long long work = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
     P.nd = nd < 1 ? 1 : nd;
     P.total = (unsigned long long)work;
@@ -356,17 +364,18 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
         for (int k = 0; k < EW_RANK; ++k) P.div_dim[k] = make_fastdiv((unsigned)P.dim[k]);
     }
     long long blocks = (work + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;   // 8 resident 256-thread CTAs per SM, grid-stride beyond
+    const long long cap = (long long)sm_count() * 16;   // resident CTAs, grid-stride beyond
     if (blocks > cap) blocks = cap;
-    int max_temp = -1;
-    for (int i = 0; i < n_instr; ++i)
-        if ((code[i].op & 3) == 3 || (code[i].op >> 2) == (ADB_EW_STORE_T >> 2)) max_temp = code[i].arg > max_temp ? code[i].arg : max_temp;
-    if (max_temp < 2) {
-        if (big) ewise_kernel<2, true><<<(unsigned)blocks, 256, 0, st>>>(P);
-        else ewise_kernel<2, false><<<(unsigned)blocks, 256, 0, st>>>(P);
+    const unsigned g = (unsigned)blocks;
+    if (max_temp < 0) {
+        if (big) ewise_kernel<8, 0, true><<<g, 256, 0, st>>>(P);
+        else ewise_kernel<8, 0, false><<<g, 256, 0, st>>>(P);
+    } else if (max_temp < 2) {
+        if (big) ewise_kernel<8, 2, true><<<g, 256, 0, st>>>(P);
+        else ewise_kernel<8, 2, false><<<g, 256, 0, st>>>(P);
     } else {
-        if (big) ewise_kernel<EW_TEMPS, true><<<(unsigned)blocks, 256, 0, st>>>(P);
-        else ewise_kernel<EW_TEMPS, false><<<(unsigned)blocks, 256, 0, st>>>(P);
+        if (big) ewise_kernel<4, EW_TEMPS, true><<<g, 256, 0, st>>>(P);
+        else ewise_kernel<4, EW_TEMPS, false><<<g, 256, 0, st>>>(P);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("ewise launch failed: %s", cudaGetErrorString(e));

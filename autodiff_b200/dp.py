@@ -14,6 +14,7 @@ import time
 
 import numpy as np
 
+from .core.engine import evaluate_many
 from .core.grad import grad
 from .core.high_level_ops import NN, Adam
 from .core.node import Variable
@@ -54,12 +55,15 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True):
     sce = SoftmaxCEWithLogits(labels=yv, logits=logits)
     cost = Einsum("i->", sce) / global_batch
     grads = grad(cost, nn.w)
-    gdev = [None] * len(grads)
     works = []
-    for i in reversed(range(len(grads))):          # last layer's dW is ready first
-        gdev[i] = grads[i].eval_device()
+
+    def ready(node):                               # fires when a gradient's kernels are queued
         if dist is not None:
-            works.append(allreduce_async(gdev[i], dist))
+            works.append(allreduce_async(node._dev, dist))
+    # one fusion plan over all outputs; last layer's dW is needed first, so it is evaluated first and its
+    # all-reduce overlaps the rest of the backward pass
+    evaluate_many(list(reversed(grads)), on_ready=ready)
+    gdev = [g.eval_device() for g in grads]
     for w in works:
         w.wait()
     new_w = opt(list(nn.w), gdev)
