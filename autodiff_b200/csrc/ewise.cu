@@ -57,40 +57,58 @@ struct Vec {
     double v[V];
 };
 
-template <int V>
-__device__ __forceinline__ Vec<V> load_in(const EwParams& P, int i, long long base, int nvalid) {
+// A thread owns V/2 element PAIRS along the innermost dimension, PS elements apart:
+//   PS = 64 ("lane-contiguous": the 32 lanes of a warp cover 512 contiguous bytes per 128-bit access; used when
+//            the innermost extent is long) or PS = 2 ("thread-contiguous": V consecutive elements per thread).
+template <int V, int PS>
+__device__ __forceinline__ Vec<V> load_in(const EwParams& P, int i, long long base, long long pos0) {
     Vec<V> r;
     const double* p = P.in[i] + base;
     const long long s0 = P.in_stride[i][0];
+    const long long dim0 = P.dim[0];
     if (s0 == 0) {
         const double x = __ldg(p);
 #pragma unroll
         for (int e = 0; e < V; ++e) r.v[e] = x;
-    } else if (((P.in_vec >> i) & 1u) && nvalid == V) {
+    } else if ((P.in_vec >> i) & 1u) {
 #pragma unroll
-        for (int e = 0; e < V / 2; ++e) {
-            const double2 a = __ldg(reinterpret_cast<const double2*>(p) + e);
-            r.v[2 * e] = a.x;
-            r.v[2 * e + 1] = a.y;
+        for (int j = 0; j < V / 2; ++j) {
+            const long long pos = pos0 + j * PS;
+            if (pos + 1 < dim0) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(p + j * PS));
+                r.v[2 * j] = a.x;
+                r.v[2 * j + 1] = a.y;
+            } else {
+                r.v[2 * j] = pos < dim0 ? __ldg(p + j * PS) : 0.0;
+                r.v[2 * j + 1] = 0.0;
+            }
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < V; ++e) r.v[e] = (e < nvalid) ? __ldg(p + e * s0) : 0.0;
+        for (int j = 0; j < V / 2; ++j) {
+            const long long pos = pos0 + j * PS;
+            r.v[2 * j] = pos < dim0 ? __ldg(p + (j * PS) * s0) : 0.0;
+            r.v[2 * j + 1] = pos + 1 < dim0 ? __ldg(p + (j * PS + 1) * s0) : 0.0;
+        }
     }
     return r;
 }
 
-template <int V>
-__device__ __forceinline__ void store_out(const EwParams& P, int j, long long base, int nvalid, const Vec<V>& a) {
-    double* p = P.out[j] + base;
-    const long long s0 = P.out_stride[j][0];
-    if (((P.out_vec >> j) & 1u) && nvalid == V) {
+template <int V, int PS>
+__device__ __forceinline__ void store_out(const EwParams& P, int jout, long long base, long long pos0, const Vec<V>& a) {
+    double* p = P.out[jout] + base;
+    const long long s0 = P.out_stride[jout][0];
+    const long long dim0 = P.dim[0];
+    const bool vec = (P.out_vec >> jout) & 1u;
 #pragma unroll
-        for (int e = 0; e < V / 2; ++e) __stcs(reinterpret_cast<double2*>(p) + e, make_double2(a.v[2 * e], a.v[2 * e + 1]));
-    } else {
-#pragma unroll
-        for (int e = 0; e < V; ++e)
-            if (e < nvalid) p[e * s0] = a.v[e];
+    for (int j = 0; j < V / 2; ++j) {
+        const long long pos = pos0 + j * PS;
+        if (vec && pos + 1 < dim0) {
+            __stcs(reinterpret_cast<double2*>(p + j * PS), make_double2(a.v[2 * j], a.v[2 * j + 1]));
+        } else {
+            if (pos < dim0) p[(j * PS) * s0] = a.v[2 * j];
+            if (pos + 1 < dim0) p[(j * PS + 1) * s0] = a.v[2 * j + 1];
+        }
     }
 }
 
@@ -99,15 +117,20 @@ __device__ __forceinline__ void store_out(const EwParams& P, int j, long long ba
 __device__ __noinline__ double ew_pow(double a, double b) { return pow(a, b); }   // keeps pow's registers out of the main loop
 
 // V elements per thread per step (V = 8: four 128-bit loads in flight per operand), NT register temps.
-template <int V, int NT, bool BIG>
+// LC: lane-contiguous pair layout (work item = one warp-wide tile of 32*V elements) vs thread-contiguous.
+template <int V, int NT, bool BIG, bool LC>
 __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel(const __grid_constant__ EwParams P) {
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < P.total; w += step) {
+    constexpr int PS = LC ? 64 : 2;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long step = LC ? nthreads / 32 : nthreads;
+    const unsigned lane = threadIdx.x & 31u;
+    for (unsigned long long w = LC ? tid / 32 : tid; w < P.total; w += step) {
         long long idx[EW_RANK];
         if (BIG) {      // >= 2^31 work items: plain 64-bit divisions
-            const long long chunks0 = (P.dim[0] + V - 1) / V;
+            const long long chunks0 = (long long)P.div_chunks0.d;
             long long o = (long long)w / chunks0;
-            idx[0] = ((long long)w - o * chunks0) * V;
+            idx[0] = ((long long)w - o * chunks0) * (LC ? 32 * V : V) + (LC ? lane * 2 : 0);
 #pragma unroll
             for (int k = 1; k < EW_RANK; ++k) {
                 const long long d = P.dim[k];
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel
         } else {
             const unsigned w32 = (unsigned)w;
             unsigned o = fastdiv(w32, P.div_chunks0);
-            idx[0] = (long long)(w32 - o * P.div_chunks0.d) * V;
+            idx[0] = (long long)(w32 - o * P.div_chunks0.d) * (LC ? 32 * V : V) + (LC ? lane * 2 : 0);
 #pragma unroll
             for (int k = 1; k < EW_RANK; ++k) {
                 if (k < P.nd) {
@@ -130,8 +153,7 @@ __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel
                 }
             }
         }
-        const long long rem = P.dim[0] - idx[0];
-        const int nvalid = rem >= V ? V : (int)rem;
+        const long long pos0 = idx[0];
 
         Vec<V> acc;
         Vec<V> t[NT > 0 ? NT : 1];
@@ -150,7 +172,7 @@ __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel
 #pragma unroll
                 for (int k = 0; k < EW_RANK; ++k)
                     if (k < P.nd) base += idx[k] * P.in_stride[arg][k];
-                x = load_in<V>(P, arg, base, nvalid);
+                x = load_in<V, PS>(P, arg, base, pos0);
             } else if (src == 2) {
 #pragma unroll
                 EW_FOR x.v[e] = imm;
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel
 #pragma unroll
                     for (int k = 0; k < EW_RANK; ++k)
                         if (k < P.nd) base += idx[k] * P.out_stride[arg][k];
-                    store_out<V>(P, arg, base, nvalid, acc);
+                    store_out<V, PS>(P, arg, base, pos0, acc);
                     break;
                 }
                 case ADB_EW_NEG >> 2:
@@ -353,30 +375,33 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
     for (int i = 0; i < n_instr; ++i)
         if ((code[i].op & 3) == 3 || (code[i].op >> 2) == (ADB_EW_STORE_T >> 2)) max_temp = code[i].arg > max_temp ? code[i].arg : max_temp;
     const int V = max_temp < 2 ? 8 : 4;
-    const long long chunks0 = (P.dim[0] + V - 1) / V;
+    const bool lc = P.dim[0] >= 32 * V;                       // long rows: warp-wide coalesced tiles
+    const long long per_item = lc ? 32 * V : V;
+    const long long chunks0 = (P.dim[0] + per_item - 1) / per_item;
     const long long work = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
     P.nd = nd < 1 ? 1 : nd;
     P.total = (unsigned long long)work;
     bool big = work >= (1LL << 31);
     for (int k = 0; k < EW_RANK; ++k) big = big || P.dim[k] >= (1LL << 31);
-    if (!big) {
-        P.div_chunks0 = make_fastdiv((unsigned)chunks0);
+    P.div_chunks0 = make_fastdiv((unsigned)(chunks0 < (1LL << 32) ? chunks0 : 0));
+    P.div_chunks0.d = (unsigned)chunks0;
+    if (chunks0 >= (1LL << 32)) return set_error("ewise: innermost extent too large");
+    if (!big)
         for (int k = 0; k < EW_RANK; ++k) P.div_dim[k] = make_fastdiv((unsigned)P.dim[k]);
-    }
-    long long blocks = (work + 255) / 256;
+    const long long threads_needed = lc ? work * 32 : work;
+    long long blocks = (threads_needed + 255) / 256;
     const long long cap = (long long)sm_count() * 16;   // resident CTAs, grid-stride beyond
     if (blocks > cap) blocks = cap;
     const unsigned g = (unsigned)blocks;
-    if (max_temp < 0) {
-        if (big) ewise_kernel<8, 0, true><<<g, 256, 0, st>>>(P);
-        else ewise_kernel<8, 0, false><<<g, 256, 0, st>>>(P);
-    } else if (max_temp < 2) {
-        if (big) ewise_kernel<8, 2, true><<<g, 256, 0, st>>>(P);
-        else ewise_kernel<8, 2, false><<<g, 256, 0, st>>>(P);
-    } else {
-        if (big) ewise_kernel<4, EW_TEMPS, true><<<g, 256, 0, st>>>(P);
-        else ewise_kernel<4, EW_TEMPS, false><<<g, 256, 0, st>>>(P);
-    }
+#define ADB_EW_LAUNCH(VV, NTT)                                                               \
+    do {                                                                                     \
+        if (big) { if (lc) ewise_kernel<VV, NTT, true, true><<<g, 256, 0, st>>>(P); else ewise_kernel<VV, NTT, true, false><<<g, 256, 0, st>>>(P); } \
+        else { if (lc) ewise_kernel<VV, NTT, false, true><<<g, 256, 0, st>>>(P); else ewise_kernel<VV, NTT, false, false><<<g, 256, 0, st>>>(P); } \
+    } while (0)
+    if (max_temp < 0) ADB_EW_LAUNCH(8, 0);
+    else if (max_temp < 2) ADB_EW_LAUNCH(8, 2);
+    else ADB_EW_LAUNCH(4, EW_TEMPS);
+#undef ADB_EW_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("ewise launch failed: %s", cudaGetErrorString(e));
     count_launch();

@@ -395,6 +395,43 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
     if (M == 1 && dd.a_sk != 1) dd.a_sm = 1;
     if (N == 1 && dd.b_sk != 1) dd.b_sn = 1;
     d = &dd;
+    // Operands TMA cannot describe (broadcast / odd pitch / unaligned base / neither stride is 1) are repacked into a
+    // dense K-contiguous workspace when the problem is large enough for the DMMA path to pay for the extra pass.
+    double* ws_a = nullptr;
+    double* ws_b = nullptr;
+    auto describable = [&](const double* p, long long s_row, long long s_k, long long s_b) {
+        const bool kc = s_k == 1, mc = !kc && s_row == 1;
+        return (kc || mc) && tma_ok(p, kc ? s_row : s_k, s_b, batch);
+    };
+    const bool big_enough = (double)M * (double)N * (double)K * (double)batch >= 16.0 * 1024 * 1024 && batch <= 65535;
+    if (force_path != 2 && big_enough && load_encode()) {
+        const long long Kp = (K + 1) & ~1LL;
+        auto repack = [&](const double* src, long long rows, long long s_row, long long s_k, long long s_b, double** ws) -> int {
+            cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(ws), (size_t)batch * rows * Kp * sizeof(double), st);
+            if (e != cudaSuccess) return set_error("gemm: workspace allocation failed: %s", cudaGetErrorString(e));
+            adb_tensor in, out;
+            in.ptr = const_cast<double*>(src); in.rank = 3;
+            in.shape[0] = batch; in.shape[1] = rows; in.shape[2] = K;
+            in.stride[0] = s_b; in.stride[1] = s_row; in.stride[2] = s_k;
+            out.ptr = *ws; out.rank = 3;
+            out.shape[0] = batch; out.shape[1] = rows; out.shape[2] = K;
+            out.stride[0] = rows * Kp; out.stride[1] = Kp; out.stride[2] = 1;
+            adb_ew_instr code[2] = {{ADB_EW_LOAD | ADB_EW_SRC_IN, 0, 0.0}, {ADB_EW_STORE_OUT, 0, 0.0}};
+            return ewise_run(code, 2, 1, &in, 1, &out, st);
+        };
+        if (!describable(dd.A, dd.a_sm, dd.a_sk, dd.a_sb)) {
+            if (int rc = repack(dd.A, M, dd.a_sm, dd.a_sk, dd.a_sb, &ws_a)) return rc;
+            dd.A = ws_a; dd.a_sm = Kp; dd.a_sk = 1; dd.a_sb = M * Kp;
+        }
+        if (!describable(dd.B, dd.b_sn, dd.b_sk, dd.b_sb)) {
+            if (int rc = repack(dd.B, N, dd.b_sn, dd.b_sk, dd.b_sb, &ws_b)) { if (ws_a) cudaFreeAsync(ws_a, st); return rc; }
+            dd.B = ws_b; dd.b_sn = Kp; dd.b_sk = 1; dd.b_sb = N * Kp;
+        }
+    }
+    struct WsGuard {
+        double *a, *b; cudaStream_t st;
+        ~WsGuard() { if (a) cudaFreeAsync(a, st); if (b) cudaFreeAsync(b, st); }
+    } guard{ws_a, ws_b, st};
     const bool a_kc = d->a_sk == 1;
     const bool a_mc = !a_kc && d->a_sm == 1;
     const bool b_kc = d->b_sk == 1;

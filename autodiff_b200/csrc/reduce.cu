@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "adb_internal.h"
 
@@ -151,6 +152,232 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(const __grid_const
     }
 }
 
+// ----------------------------------------------------------------------------- fast path (<= 3 output dims, <= 2 summed dims)
+// The summed space is flattened to rho in [0, R0*R1) and decoded with multiply-shift divisors; every lane keeps
+// four independent (optionally 128-bit) loads per operand in flight, so short inner extents (R0 = 128 in the
+// 'ijkl,jl->ik' sweep member) no longer serialise on one load per step.
+struct FastDiv32 {
+    unsigned mul, shr, d, _pad;
+};
+static FastDiv32 make_fd(unsigned d) {
+    FastDiv32 f;
+    f.d = d; f._pad = 0;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+    unsigned lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const unsigned p = 31 + lg;
+    f.mul = (unsigned)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+    return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv32& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+
+struct Red2Params {
+    int n_ops, square, splits, _pad;
+    unsigned O, R, chunk, _pad2;
+    FastDiv32 odiv[3];
+    FastDiv32 r0div;
+    long long out_s[3];
+    long long op_os[ADB_RED_MAX_OPS][3];
+    long long op_r0s[ADB_RED_MAX_OPS], op_r1s[ADB_RED_MAX_OPS];
+    const double* op[ADB_RED_MAX_OPS];
+    double* out;
+    double* partial;
+};
+
+template <int G, int NOPS, int VEC>
+__global__ void __launch_bounds__(256) reduce2_kernel(const __grid_constant__ Red2Params P) {
+    constexpr int GROUPS = 256 / G;
+    constexpr int UNROLL = 4;
+    const int lane = threadIdx.x % G;
+    const unsigned z = blockIdx.y;
+    const unsigned lo = z * P.chunk;
+    const unsigned hi = (lo + P.chunk < P.R) ? lo + P.chunk : P.R;
+    __shared__ double warp_part[8];
+
+    for (unsigned o = blockIdx.x * GROUPS + threadIdx.x / G; o < P.O; o += gridDim.x * GROUPS) {
+        // decode the output index
+        unsigned rem = o;
+        long long out_off = 0;
+        const double* base[NOPS];
+#pragma unroll
+        for (int t = 0; t < NOPS; ++t) base[t] = P.op[t];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned qn = fd_div(rem, P.odiv[k]);
+            const unsigned i = rem - qn * P.odiv[k].d;
+            rem = qn;
+            out_off += (long long)i * P.out_s[k];
+#pragma unroll
+            for (int t = 0; t < NOPS; ++t) base[t] += (long long)i * P.op_os[t][k];
+        }
+        double acc0 = 0.0, acc1 = 0.0;
+        for (unsigned r = lo + lane * VEC; r < hi; r += UNROLL * G * VEC) {
+            double v0[UNROLL], v1[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const unsigned rho = r + u * G * VEC;
+                v0[u] = 0.0; v1[u] = 0.0;
+                if (rho < hi) {
+                    const unsigned r1 = fd_div(rho, P.r0div);
+                    const unsigned r0 = rho - r1 * P.r0div.d;
+                    if (VEC == 2) {
+                        double2 a;
+                        {
+                            const double* p = base[0] + (long long)r0 * P.op_r0s[0] + (long long)r1 * P.op_r1s[0];
+                            if (P.op_r0s[0] == 0) { const double s = __ldg(p); a = make_double2(s, s); }
+                            else a = __ldg(reinterpret_cast<const double2*>(p));
+                        }
+                        if (NOPS == 1 && P.square) { a.x *= a.x; a.y *= a.y; }
+#pragma unroll
+                        for (int t = 1; t < NOPS; ++t) {
+                            const double* p = base[t] + (long long)r0 * P.op_r0s[t] + (long long)r1 * P.op_r1s[t];
+                            double2 b;
+                            if (P.op_r0s[t] == 0) { const double s = __ldg(p); b = make_double2(s, s); }
+                            else b = __ldg(reinterpret_cast<const double2*>(p));
+                            a.x *= b.x; a.y *= b.y;
+                        }
+                        v0[u] = a.x; v1[u] = a.y;
+                    } else {
+                        double a = __ldg(base[0] + (long long)r0 * P.op_r0s[0] + (long long)r1 * P.op_r1s[0]);
+                        if (NOPS == 1 && P.square) a *= a;
+#pragma unroll
+                        for (int t = 1; t < NOPS; ++t) a *= __ldg(base[t] + (long long)r0 * P.op_r0s[t] + (long long)r1 * P.op_r1s[t]);
+                        v0[u] = a;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) { acc0 += v0[u]; if (VEC == 2) acc1 += v1[u]; }
+        }
+        double acc = acc0 + acc1;
+        if (G > 1) {
+#pragma unroll
+            for (int off = (G > 32 ? 16 : G / 2); off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, G > 32 ? 32 : G);
+        }
+        if (G == 256) {
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                acc = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) acc += warp_part[w];
+            }
+        }
+        if (lane == 0) {
+            if (P.splits == 1) P.out[out_off] = acc;
+            else P.partial[(long long)z * P.O + o] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce2_finalize_kernel(const __grid_constant__ Red2Params P) {
+    for (unsigned o = blockIdx.x * blockDim.x + threadIdx.x; o < P.O; o += gridDim.x * blockDim.x) {
+        unsigned rem = o;
+        long long out_off = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned qn = fd_div(rem, P.odiv[k]);
+            out_off += (long long)(rem - qn * P.odiv[k].d) * P.out_s[k];
+            rem = qn;
+        }
+        double acc = 0.0;
+        for (int z = 0; z < P.splits; ++z) acc += P.partial[(long long)z * P.O + o];
+        P.out[out_off] = acc;
+    }
+}
+
+template <int G, int VEC>
+static void launch_reduce2(const Red2Params& P, dim3 grid, cudaStream_t st) {
+    switch (P.n_ops) {
+        case 1: reduce2_kernel<G, 1, VEC><<<grid, 256, 0, st>>>(P); break;
+        case 2: reduce2_kernel<G, 2, VEC><<<grid, 256, 0, st>>>(P); break;
+        case 3: reduce2_kernel<G, 3, VEC><<<grid, 256, 0, st>>>(P); break;
+        default: reduce2_kernel<G, 4, VEC><<<grid, 256, 0, st>>>(P); break;
+    }
+}
+
+// Returns 0 = ran, -1 = not applicable (caller falls back to the generic kernel), >0 = error.
+static int reduce2_try(const ReduceSpec& S, cudaStream_t st) {
+    if (S.n_o > 3 || S.n_r > 2) return -1;
+    long long O = 1, R = 1;
+    for (int k = 0; k < S.n_o; ++k) O *= S.odim[k];
+    for (int k = 0; k < S.n_r; ++k) R *= S.rdim[k];
+    if (O <= 0) return 0;
+    if (O >= (1LL << 31) || R >= (1LL << 31) || R <= 0) return -1;
+    Red2Params P;
+    memset(&P, 0, sizeof P);
+    P.n_ops = S.n_ops; P.square = S.square;
+    P.O = (unsigned)O; P.R = (unsigned)R;
+    for (int k = 0; k < 3; ++k) {
+        P.odiv[k] = make_fd(k < S.n_o ? (unsigned)S.odim[k] : 1u);
+        P.out_s[k] = k < S.n_o ? S.out_s[k] : 0;
+        for (int t = 0; t < S.n_ops; ++t) P.op_os[t][k] = k < S.n_o ? S.op_os[t][k] : 0;
+    }
+    const long long R0 = S.n_r > 0 ? S.rdim[0] : 1;
+    P.r0div = make_fd((unsigned)R0);
+    for (int t = 0; t < S.n_ops; ++t) {
+        P.op_r0s[t] = S.n_r > 0 ? S.op_rs[t][0] : 0;
+        P.op_r1s[t] = S.n_r > 1 ? S.op_rs[t][1] : 0;
+        P.op[t] = S.op[t];
+    }
+    P.out = S.out;
+    const bool row = S.group > 1;
+    int G = 1;
+    if (row) G = (O < 2 * 148) ? 256 : 32;
+    if (!row && O < 4 * 148) G = (O < 64) ? 256 : 32;     // few outputs: cooperate on each even if strided
+    // 128-bit loads along the flattened summed index
+    int VEC = 1;
+    if (G > 1 && (R0 % 2) == 0) {
+        VEC = 2;
+        for (int t = 0; t < S.n_ops && VEC == 2; ++t) {
+            if (P.op_r0s[t] != 0 && P.op_r0s[t] != 1) VEC = 1;
+            if (P.op_r1s[t] & 1) VEC = 1;
+            for (int k = 0; k < 3; ++k) if (P.op_os[t][k] & 1) VEC = 1;
+            if (reinterpret_cast<uintptr_t>(P.op[t]) & 15) VEC = 1;
+        }
+    }
+    const long long groups_per_block = 256 / G;
+    long long blocks_x = (O + groups_per_block - 1) / groups_per_block;
+    const long long target = 148LL * 8;
+    long long splits = 1;
+    const long long per_iter = (long long)G * VEC * 4;          // summed elements one group covers per loop trip
+    if (blocks_x < target) {
+        splits = (target + blocks_x - 1) / blocks_x;
+        const long long max_splits = R / (per_iter * 2) > 0 ? R / (per_iter * 2) : 1;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 2048) splits = 2048;
+    }
+    if (blocks_x > target * 8) blocks_x = target * 8;
+    long long chunk = (R + splits - 1) / splits;
+    chunk = (chunk + per_iter - 1) / per_iter * per_iter;        // keeps 128-bit loads aligned across splits
+    splits = (R + chunk - 1) / chunk;
+    P.chunk = (unsigned)chunk;
+    P.splits = (int)splits;
+    if (splits > 1) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&P.partial), (size_t)splits * O * sizeof(double), st);
+        if (e != cudaSuccess) return set_error("reduce: workspace allocation failed: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)blocks_x, (unsigned)splits, 1);
+    if (G == 256) { if (VEC == 2) launch_reduce2<256, 2>(P, grid, st); else launch_reduce2<256, 1>(P, grid, st); }
+    else if (G == 32) { if (VEC == 2) launch_reduce2<32, 2>(P, grid, st); else launch_reduce2<32, 1>(P, grid, st); }
+    else launch_reduce2<1, 1>(P, grid, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("reduce2 launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    if (splits > 1) {
+        long long fb = (O + 255) / 256;
+        if (fb > 148 * 8) fb = 148 * 8;
+        reduce2_finalize_kernel<<<(unsigned)fb, 256, 0, st>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error("reduce2 finalize launch failed: %s", cudaGetErrorString(e));
+        count_launch();
+        cudaFreeAsync(P.partial, st);
+    }
+    return 0;
+}
+
 template <int G>
 static void launch_reduce(const RedParams& P, dim3 grid, cudaStream_t st) {
     switch (P.n_ops) {
@@ -164,6 +391,10 @@ static void launch_reduce(const RedParams& P, dim3 grid, cudaStream_t st) {
 // dims are given innermost-first and already collapsed by the planner.
 int reduce_run(const ReduceSpec& S, cudaStream_t st) {
     if (S.n_ops < 1 || S.n_ops > ADB_RED_MAX_OPS) return set_error("reduce: %d operands (max %d)", S.n_ops, ADB_RED_MAX_OPS);
+    {
+        const int rc = reduce2_try(S, st);
+        if (rc >= 0) return rc;
+    }
     RedParams P;
     P.n_ops = S.n_ops;
     P.square = S.square;
