@@ -10,5 +10,6 @@ from .core.ops import *            # noqa: F401,F403
 from .core.reshape import *        # noqa: F401,F403
 from .core.high_level_ops import * # noqa: F401,F403
 from .core.wrappers import checkpoint
+from .core.conv import Col2Im, Conv2D, Im2Col
 from .core.grad import grad
-from .device import DeviceArray, init, launch_count, pinned_empty, synchronize, to_device, to_host
+from .device import DeviceArray, init, launch_count, pinned_empty, synchronize, to_device, to_host, use_stream

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "adb_reduce_sum": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "adb_sum_squares": (C.c_int, [C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "adb_softmax_ce": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
+    "adb_im2col": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
+    "adb_col2im": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
 }
 
 _lib = None
@@ -86,7 +88,7 @@ def lib():
 def check(rc):
     if rc != 0:
         msg = lib().adb_last_error().decode("utf-8", "replace")
-        if msg.startswith("einsum:") or msg.startswith("Number of operands") or msg.startswith("ewise:") or msg.startswith("softmax_ce:"):
+        if msg.startswith("einsum:") or msg.startswith("Number of operands") or msg.startswith("ewise:") or msg.startswith("softmax_ce:") or msg.startswith("im2col:") or msg.startswith("col2im:"):
             raise ValueError(msg)
         raise BackendError(msg)
 

@@ -186,30 +186,41 @@ def check_pending_flags():
 
 
 # ------------------------------------------------------------------------------------------- program helper
+_prog_cache = {}
+
+
+def _program(code):
+    """ctypes instruction array for a program, cached by content (programs repeat every training step)."""
+    key = tuple(code)
+    prog = _prog_cache.get(key)
+    if prog is None:
+        n = len(key)
+        if n > _lib.EW_MAX_INSTR:
+            raise ValueError("elementwise program too long (%d instructions)" % n)
+        prog = (_lib.EwInstr * n)()
+        for i, (op, arg, imm) in enumerate(key):
+            prog[i].op = op
+            prog[i].arg = arg
+            prog[i].imm = imm
+        if len(_prog_cache) > 8192:
+            _prog_cache.clear()
+        _prog_cache[key] = prog
+    return prog
+
+
 def run_program(code, inputs, out_shape, n_out=1):
     """code: list of (op, arg, imm); inputs: list of DeviceArray; returns the output DeviceArray(s)."""
-    n = len(code)
-    if n > _lib.EW_MAX_INSTR:
-        raise ValueError("elementwise program too long (%d instructions)" % n)
-    prog = (_lib.EwInstr * n)()
-    for i, (op, arg, imm) in enumerate(code):
-        prog[i].op = op
-        prog[i].arg = arg
-        prog[i].imm = imm
     outs = [DeviceArray.empty(out_shape) for _ in range(n_out)]
-    tin = (_lib.Tensor * max(len(inputs), 1))(*[a.tensor() for a in inputs])
-    tout = (_lib.Tensor * n_out)(*[o.tensor() for o in outs])
-    _lib.check(_lib.lib().adb_ewise(prog, n, len(inputs), tin, n_out, tout, C.c_void_p(stream_ptr())))
+    run_program_into(code, inputs, outs)
     return outs[0] if n_out == 1 else outs
 
 
 def run_program_into(code, inputs, outs):
-    n = len(code)
-    prog = (_lib.EwInstr * n)()
-    for i, (op, arg, imm) in enumerate(code):
-        prog[i].op = op
-        prog[i].arg = arg
-        prog[i].imm = imm
+    prog = _program(code)
     tin = (_lib.Tensor * max(len(inputs), 1))(*[a.tensor() for a in inputs])
     tout = (_lib.Tensor * len(outs))(*[o.tensor() for o in outs])
-    _lib.check(_lib.lib().adb_ewise(prog, n, len(inputs), tin, len(outs), tout, C.c_void_p(stream_ptr())))
+    _lib.check(_lib.lib().adb_ewise(prog, len(prog), len(inputs), tin, len(outs), tout, _STREAM()))
+
+
+def _STREAM():
+    return C.c_void_p(stream_ptr())

@@ -149,18 +149,22 @@ class Emitter:
             if not kids:
                 self._emit(_lib.EW_LOAD | IMM, 0, float(identity))
                 return
-            # nested operands are evaluated into temps first so the left-to-right association is kept;
-            # a lone nested operand in first position can stay in acc.
-            n_sub = sum(1 for ch in kids if self.operand(ch)[0] == "sub")
-            resolved, transient = [], []
-            for i, ch in enumerate(kids):
-                o = self.operand(ch)
-                if o[0] == "sub" and not (i == 0 and n_sub == 1):
-                    t, tr = self.into_temp(ch)
+            # Nested operands other than the first are evaluated into temps BEFORE the fold starts, so the
+            # left-to-right association ((k0 op k1) op k2) is kept; the first operand is evaluated last and
+            # stays in acc (saves one temp and a STORE/LOAD pair).
+            resolved, transient = [None] * len(kids), []
+            for i in range(len(kids) - 1, 0, -1):
+                o = self.operand(kids[i])
+                if o[0] == "sub":
+                    t, tr = self.into_temp(kids[i])
                     o = ("tmp", t)
                     if tr:
                         transient.append(t)
-                resolved.append(o)
+                resolved[i] = o
+            resolved[0] = self.operand(kids[0])
+            for i in range(1, len(kids)):            # sharing may have turned an input into a temp meanwhile
+                if resolved[i][0] != "tmp":
+                    resolved[i] = self.operand(kids[i])
             if resolved[0][0] == "sub":
                 self.value(kids[0])
             else:

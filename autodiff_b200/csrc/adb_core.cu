@@ -37,6 +37,14 @@ int adb_init(int device) {
     cudaDeviceProp p;
     ADB_CUDA_OK(cudaGetDeviceProperties(&p, device));
     if (p.major != 10) return adb::set_error("adb_init: device %s is sm_%d%d; this library is built for sm_100a only", p.name, p.major, p.minor);
+    // keep freed workspaces in the stream-ordered pool: the default threshold (0) hands memory back to the driver at
+    // every synchronisation, which turns each cudaMallocAsync after a sync into a millisecond-scale allocation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     return 0;
 }
 

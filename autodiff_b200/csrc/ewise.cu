@@ -177,10 +177,17 @@ __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel
 #pragma unroll
                 EW_FOR x.v[e] = imm;
             } else if (src == 3) {
-                // temps live in registers: selected by uniform compares, never by dynamic indexing
-#pragma unroll
-                for (int k = 0; k < NT; ++k)
-                    if (arg == k) x = t[k];
+                // temps live in registers: selected by a uniform branch, never by dynamic indexing
+                switch (arg) {
+                    case 0: if (NT > 0) x = t[0]; break;
+                    case 1: if (NT > 1) x = t[1 % (NT > 0 ? NT : 1)]; break;
+                    case 2: if (NT > 2) x = t[2 % (NT > 0 ? NT : 1)]; break;
+                    case 3: if (NT > 3) x = t[3 % (NT > 0 ? NT : 1)]; break;
+                    case 4: if (NT > 4) x = t[4 % (NT > 0 ? NT : 1)]; break;
+                    case 5: if (NT > 5) x = t[5 % (NT > 0 ? NT : 1)]; break;
+                    case 6: if (NT > 6) x = t[6 % (NT > 0 ? NT : 1)]; break;
+                    default: if (NT > 7) x = t[7 % (NT > 0 ? NT : 1)]; break;
+                }
             }
             switch (op >> 2) {
                 case ADB_EW_LOAD >> 2:
@@ -212,9 +219,16 @@ __global__ void __launch_bounds__(256, (V == 8 && NT == 0) ? 3 : 2) ewise_kernel
                     EW_FOR acc.v[e] = fmax(acc.v[e], x.v[e]);
                     break;
                 case ADB_EW_STORE_T >> 2:
-#pragma unroll
-                    for (int k = 0; k < NT; ++k)
-                        if (arg == k) t[k] = acc;
+                    switch (arg) {
+                        case 0: if (NT > 0) t[0] = acc; break;
+                        case 1: if (NT > 1) t[1 % (NT > 0 ? NT : 1)] = acc; break;
+                        case 2: if (NT > 2) t[2 % (NT > 0 ? NT : 1)] = acc; break;
+                        case 3: if (NT > 3) t[3 % (NT > 0 ? NT : 1)] = acc; break;
+                        case 4: if (NT > 4) t[4 % (NT > 0 ? NT : 1)] = acc; break;
+                        case 5: if (NT > 5) t[5 % (NT > 0 ? NT : 1)] = acc; break;
+                        case 6: if (NT > 6) t[6 % (NT > 0 ? NT : 1)] = acc; break;
+                        default: if (NT > 7) t[7 % (NT > 0 ? NT : 1)] = acc; break;
+                    }
                     break;
                 case ADB_EW_STORE_OUT >> 2: {
                     long long base = 0;

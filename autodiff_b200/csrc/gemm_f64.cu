@@ -29,15 +29,24 @@
 
 namespace adb {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 6;
-constexpr int A_TILE_BYTES = BM * BK * 8;   // 16 KiB
-constexpr int B_TILE_BYTES = BN * BK * 8;   // 16 KiB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int BK = 16;
+// Tile configuration: 8 warps as 2 (M) x 4 (N); warp tile = (BM/2) x (BN/4) = MT x NT fragments of 8x8.
+//   Big   128x128, 6 stages, 1 CTA/SM  : large contractions (C2a/C2b/C3)
+//   Small  64x64,  6 stages, 2 CTAs/SM : problems with fewer than one wave of 128x128 tiles (char-rnn steps)
+template <int BM_, int BN_, int STAGES_, int MINB_>
+struct TileCfg {
+    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int MT = BM_ / 16, NT = BN_ / 32;        // fragments per warp
+    static constexpr int A_TILE_BYTES = BM_ * BK * 8;
+    static constexpr int B_TILE_BYTES = BN_ * BK * 8;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int PREFETCH = STAGES_ - 2;              // the slot refilled at step kt was released at kt-2: no stall
+    static constexpr int SMEM = STAGES_ * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES_ * 8;
+};
+using CfgBig = TileCfg<128, 128, 6, 1>;
+using CfgSmall = TileCfg<64, 64, 6, 2>;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = CONSUMER_WARPS * 32;   // 9 warps would round to 12 for register allocation (168 regs)
-constexpr int PREFETCH = STAGES - 2;                   // the slot refilled at step kt was released at kt-2: no stall
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
 
 // ----------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,9 +98,11 @@ struct GemmParams {
 };
 
 // ----------------------------------------------------------------------------- TMA + DMMA kernel
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <class Cfg, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
+    constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, PREFETCH = Cfg::PREFETCH;
     extern __shared__ unsigned char smem_raw[];
     // keep the pointer derived from the __shared__ array so loads compile to LDS (not generic LD)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -153,22 +164,22 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kt = 0; kt < npre; ++kt) issue_tile(kt);
     }
 
-    // ===== consumers: 2 (M) x 4 (N) warps, warp tile 64 x 32 =====
+    // ===== consumers: 2 (M) x 4 (N) warps, warp tile (BM/2) x (BN/4) =====
     const int warp_m = warp & 1;
     const int warp_n = warp >> 1;
     const int g = lane >> 2;
     const int q = lane & 3;
     const int rmap = (g >> 1) | ((g & 1) << 2);
 
-    double acc[8][4][2];
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // per-thread byte offsets inside a stage
-    const int a_off = A_KC ? (warp_m * 64 + rmap) * 128 : warp_m * 4 * 2048;
-    const int b_off = A_TILE_BYTES + (B_KC ? (warp_n * 32 + rmap) * 128 : warp_n * 2 * 2048);
+    const int a_off = A_KC ? (warp_m * (BM / 2) + rmap) * 128 : warp_m * (MT / 2) * 2048;
+    const int b_off = A_TILE_BYTES + (B_KC ? (warp_n * (BN / 4) + rmap) * 128 : warp_n * (NT / 2) * 2048);
 
     for (int kt = 0; kt < num_kt; ++kt) {
         if (is_producer && kt + PREFETCH < num_kt) issue_tile(kt + PREFETCH);
@@ -181,11 +192,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const unsigned char* sB = st + b_off;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            double a[2][8], b[2][4];
+            double a[2][MT], b[2][NT];
             if (A_KC) {
                 const int ch = ((4 * h + q) ^ rmap) << 4;
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
                     const double2 v = lds128(sA + mt * 1024 + ch);
                     a[0][mt] = v.x;
                     a[1][mt] = v.y;
@@ -196,7 +207,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int kr = 8 * h + 2 * q + pp;
                     const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
 #pragma unroll
-                    for (int blk = 0; blk < 4; ++blk) {
+                    for (int blk = 0; blk < MT / 2; ++blk) {
                         const double2 v = lds128(sA + blk * 2048 + off);
                         a[pp][2 * blk] = v.x;
                         a[pp][2 * blk + 1] = v.y;
@@ -206,7 +217,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (B_KC) {
                 const int ch = ((4 * h + q) ^ rmap) << 4;
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
+                for (int nt = 0; nt < NT; ++nt) {
                     const double2 v = lds128(sB + nt * 1024 + ch);
                     b[0][nt] = v.x;
                     b[1][nt] = v.y;
@@ -217,7 +228,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int kr = 8 * h + 2 * q + pp;
                     const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
 #pragma unroll
-                    for (int blk = 0; blk < 2; ++blk) {
+                    for (int blk = 0; blk < NT / 2; ++blk) {
                         const double2 v = lds128(sB + blk * 2048 + off);
                         b[pp][2 * blk] = v.x;
                         b[pp][2 * blk + 1] = v.y;
@@ -227,9 +238,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt)
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
+                    for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -238,24 +249,24 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
     double* __restrict__ Cb = p.C + (long long)batch * p.c_sb;
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
-        const int row = m0 + warp_m * 64 + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
+    for (int mt = 0; mt < MT; ++mt) {
+        const int row = m0 + warp_m * (BM / 2) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
         if (row >= p.M) continue;
         double* crow = Cb + (long long)row * p.c_sm;
         if (B_KC) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int col = n0 + warp_n * 32 + nt * 8 + q + 4 * e;
+                    const int col = n0 + warp_n * (BN / 4) + nt * 8 + q + 4 * e;
                     if (col < p.N) crow[(long long)col * p.c_sn] = acc[mt][nt][e];
                 }
             }
         } else {
 #pragma unroll
-            for (int blk = 0; blk < 2; ++blk) {
+            for (int blk = 0; blk < NT / 2; ++blk) {
                 // thread owns 4 consecutive columns: 4q + {0,1,2,3} = (e=0,j=0),(e=0,j=1),(e=1,j=0),(e=1,j=1)
-                const int col = n0 + warp_n * 32 + blk * 16 + 4 * q;
+                const int col = n0 + warp_n * (BN / 4) + blk * 16 + 4 * q;
                 const double v0 = acc[mt][2 * blk][0], v1 = acc[mt][2 * blk + 1][0];
                 const double v2 = acc[mt][2 * blk][1], v3 = acc[mt][2 * blk + 1][1];
                 double* cp = crow + (long long)col * p.c_sn;
@@ -364,10 +375,11 @@ static bool tma_ok(const double* base, long long s_other, long long s_batch, lon
     return true;
 }
 
-template <bool A_KC, bool B_KC>
+template <class Cfg, bool A_KC, bool B_KC>
 static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = gemm_tma_kernel<A_KC, B_KC>;
+    auto kern = gemm_tma_kernel<Cfg, A_KC, B_KC>;
+    constexpr int GEMM_SMEM = Cfg::SMEM;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -439,30 +451,40 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
     bool use_tma = force_path != 2 && (a_kc || a_mc) && (b_kc || b_mc) && batch <= 65535 && load_encode();
     if (use_tma)
         use_tma = tma_ok(d->A, a_kc ? d->a_sm : d->a_sk, d->a_sb, batch) && tma_ok(d->B, b_kc ? d->b_sn : d->b_sk, d->b_sb, batch);
-    if (force_path == 1 && !use_tma) return set_error("gemm: TMA path forced but operands are not TMA-describable");
+    if ((force_path == 1 || force_path >= 3) && !use_tma) return set_error("gemm: TMA path forced but operands are not TMA-describable");
 
     if (use_tma) {
         CUtensorMap ta, tb;
         bool ok;
         const long long a_bs = batch > 1 ? d->a_sb : 2, b_bs = batch > 1 ? d->b_sb : 2;
-        if (a_kc) ok = make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, BM);
+        // fewer than one wave of 128x128 tiles: quarter-size tiles keep more SMs busy
+        const long long big_tiles = ((M + 127) / 128) * ((N + 127) / 128) * batch;
+        const bool small = force_path == 3 || (force_path != 4 && big_tiles < 148);
+        const int bm = small ? CfgSmall::BM : CfgBig::BM, bn = small ? CfgSmall::BN : CfgBig::BN;
+        if (a_kc) ok = make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, bm);
         else      ok = make_tmap(&ta, d->A, M, K, batch, d->a_sk, a_bs, 16, BK);
         if (ok) {
-            if (b_kc) ok = make_tmap(&tb, d->B, K, N, batch, d->b_sn, b_bs, BK, BN);
+            if (b_kc) ok = make_tmap(&tb, d->B, K, N, batch, d->b_sn, b_bs, BK, bn);
             else      ok = make_tmap(&tb, d->B, N, K, batch, d->b_sk, b_bs, 16, BK);
         }
         if (ok) {
             GemmParams p;
             p.M = (int)M; p.N = (int)N; p.K = (int)K;
-            p.tiles_m = (int)((M + BM - 1) / BM);
-            p.tiles_n = (int)((N + BN - 1) / BN);
+            p.tiles_m = (int)((M + bm - 1) / bm);
+            p.tiles_n = (int)((N + bn - 1) / bn);
             p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb;
-            if (a_kc && b_kc) return launch_tma<true, true>(ta, tb, p, (int)batch, st);
-            if (a_kc && !b_kc) return launch_tma<true, false>(ta, tb, p, (int)batch, st);
-            if (!a_kc && b_kc) return launch_tma<false, true>(ta, tb, p, (int)batch, st);
-            return launch_tma<false, false>(ta, tb, p, (int)batch, st);
+            if (small) {
+                if (a_kc && b_kc) return launch_tma<CfgSmall, true, true>(ta, tb, p, (int)batch, st);
+                if (a_kc && !b_kc) return launch_tma<CfgSmall, true, false>(ta, tb, p, (int)batch, st);
+                if (!a_kc && b_kc) return launch_tma<CfgSmall, false, true>(ta, tb, p, (int)batch, st);
+                return launch_tma<CfgSmall, false, false>(ta, tb, p, (int)batch, st);
+            }
+            if (a_kc && b_kc) return launch_tma<CfgBig, true, true>(ta, tb, p, (int)batch, st);
+            if (a_kc && !b_kc) return launch_tma<CfgBig, true, false>(ta, tb, p, (int)batch, st);
+            if (!a_kc && b_kc) return launch_tma<CfgBig, false, true>(ta, tb, p, (int)batch, st);
+            return launch_tma<CfgBig, false, false>(ta, tb, p, (int)batch, st);
         }
-        if (force_path == 1) return set_error("gemm: cuTensorMapEncodeTiled rejected the operands");
+        if (force_path == 1 || force_path >= 3) return set_error("gemm: cuTensorMapEncodeTiled rejected the operands");
     }
     // generic path
     for (long long b0 = 0; b0 < batch; b0 += 65535) {

@@ -45,8 +45,21 @@ def _ensure_init():
         init()
 
 
+_stream = None
+
+
 def stream_ptr():
-    return torch().cuda.current_stream().cuda_stream
+    """cudaStream_t every kernel of this process is queued on (torch's current stream at init; see use_stream)."""
+    global _stream
+    if _stream is None:
+        _stream = torch().cuda.current_stream().cuda_stream
+    return _stream
+
+
+def use_stream(stream=None):
+    """Re-reads (or sets) the stream after the caller switched torch's current stream."""
+    global _stream
+    _stream = (stream if stream is not None else torch().cuda.current_stream()).cuda_stream
 
 
 def synchronize():
@@ -71,13 +84,14 @@ def _dense_strides(shape, pitch=None):
 
 class DeviceArray:
     """fp64 strided view of device memory.  strides are in ELEMENTS and may be 0 (broadcast) or negative."""
-    __slots__ = ("base", "offset", "shape", "strides")
+    __slots__ = ("base", "offset", "shape", "strides", "_tensor")
 
     def __init__(self, base, offset, shape, strides):
         self.base = base            # torch.float64 cuda tensor that owns the storage
         self.offset = int(offset)   # elements from base.data_ptr()
         self.shape = tuple(int(s) for s in shape)
         self.strides = tuple(int(s) for s in strides)
+        self._tensor = None         # cached adb_tensor (views are immutable)
 
     # ---- construction
     @staticmethod
@@ -133,7 +147,10 @@ class DeviceArray:
         return n
 
     def tensor(self):
-        return _lib.make_tensor(self.ptr, self.shape, self.strides)
+        t = self._tensor
+        if t is None:
+            t = self._tensor = _lib.make_tensor(self.ptr, self.shape, self.strides)
+        return t
 
     def is_dense(self):
         """C-contiguous with no padding."""

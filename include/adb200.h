@@ -65,7 +65,8 @@ ADB_API int adb_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, 
 
 /* ---- contraction: replaces np.einsum at reference autodiff/core/ops.py:180 ---------------------- */
 ADB_API int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
-/* path: 0 = auto, 1 = force TMA+DMMA kernel (error if not describable), 2 = force generic kernel */
+/* path: 0 = auto, 1 = force TMA+DMMA kernel (error if not describable), 2 = force generic kernel,
+ * 3 = force TMA+DMMA with 64x64 tiles, 4 = force TMA+DMMA with 128x128 tiles */
 ADB_API int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
 
 
@@ -133,6 +134,13 @@ ADB_API int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* strea
  *      out: rows elements (stride out_stride).  *flag (device int) is OR-ed with 1 when a label row does
  *      not sum to 1 within np.allclose tolerance (ops.py:246-248); the host raises ValueError. */
 ADB_API int adb_softmax_ce(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, void* stream);
+
+/* ---- convolution = im2col + einsum.  The reference has only a commented-out design
+ *      (reshape.py:137-160 AsStrided windows, high_level_ops.py:152-165 Convolution); semantics from its dead test
+ *      tests/test_convolution.py:17-33: NHWC, VALID, stride 1, cross-correlation, filters last.
+ *      x: (N,H,W,C) view; cols: (N*OH*OW, kh*kw*C).  col2im is the adjoint (gradient) of im2col. */
+ADB_API int adb_im2col(const adb_tensor* x, int kh, int kw, const adb_tensor* cols, void* stream);
+ADB_API int adb_col2im(const adb_tensor* cols, int kh, int kw, const adb_tensor* dx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -708,3 +708,54 @@ def conv_valid_nhwc(x, w):
     s = x.strides
     win = as_strided(x, shape=(n, oh, ow, kh, kw, c), strides=(s[0], s[1], s[2], s[1], s[2], s[3]))
     return np.einsum("nhwabc,abco->nhwo", win, w)
+
+
+class Im2Col(Node):
+    """Window gather as the reference's AsStrided design would do it (reshape.py:137-160), then flattened."""
+    def __init__(self, node, kh, kw, name="Im2Col"):
+        super().__init__([node], name)
+        self.node = self.children[0]
+        self.kh, self.kw = kh, kw
+        n, h, w, c = self.node.shape
+        self.shape = (n * (h - kh + 1) * (w - kw + 1), kh * kw * c)
+
+    def _eval(self):
+        from numpy.lib.stride_tricks import as_strided
+        x = np.ascontiguousarray(self.node())
+        n, h, w, c = x.shape
+        oh, ow = h - self.kh + 1, w - self.kw + 1
+        s = x.strides
+        win = as_strided(x, shape=(n, oh, ow, self.kh, self.kw, c), strides=(s[0], s[1], s[2], s[1], s[2], s[3]))
+        return win.reshape(self.shape)
+
+    def _partial_derivative(self, wrt, previous_grad):
+        return Col2Im(previous_grad, tuple(self.node.shape), self.kh, self.kw) if self.node == wrt else 0
+
+
+class Col2Im(Node):
+    def __init__(self, node, image_shape, kh, kw, name="Col2Im"):
+        super().__init__([node], name)
+        self.node = self.children[0]
+        self.kh, self.kw = kh, kw
+        self.shape = tuple(image_shape)
+
+    def _eval(self):
+        n, h, w, c = self.shape
+        oh, ow = h - self.kh + 1, w - self.kw + 1
+        g = np.broadcast_to(self.node(), (n * oh * ow, self.kh * self.kw * c)).reshape(n, oh, ow, self.kh, self.kw, c)
+        out = np.zeros(self.shape)
+        for a in range(self.kh):
+            for b in range(self.kw):
+                out[:, a:a + oh, b:b + ow, :] += g[:, :, :, a, b, :]
+        return out
+
+    def _partial_derivative(self, wrt, previous_grad):
+        return Im2Col(previous_grad, self.kh, self.kw) if self.node == wrt else 0
+
+
+@module_wrapper
+def Conv2D(x, w):
+    kh, kw, c, o = w.shape
+    n, h, wd, _ = x.shape
+    out = Einsum("pk,ko->po", Im2Col(x, kh, kw), Reshape(w, (kh * kw * c, o)))
+    return Reshape(out, (n, h - kh + 1, wd - kw + 1, o))

@@ -284,7 +284,7 @@ def test_gemm_c_abi_all_layouts(ad):
                 d.b_sk, d.b_sn, d.b_sb = (1, K, N * K) if b_kc else (N, 1, N * K)
                 d.c_sm, d.c_sn, d.c_sb = N, 1, M * N
                 aligned = (K % 2 == 0 if a_kc else M % 2 == 0) and (K % 2 == 0 if b_kc else N % 2 == 0)
-                for path in ((1, 2) if aligned else (0, 2)):
+                for path in ((1, 2, 3, 4) if aligned else (0, 2)):
                     Ct.fill_(float("nan"))
                     _lib.check(_lib.lib().adb_gemm_f64_path(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream), path))
                     torch.cuda.synchronize()
@@ -306,3 +306,48 @@ def test_large_gemm_properties(ad):
     rhs = a.sum(0) @ b.sum(1)
     assert abs(lhs - rhs) <= 1e-9 * abs(rhs) + 1e-6
     check(c[:64], a[:64] @ b, tol=1e-12)
+
+
+def test_conv_im2col_forward_and_grads(ad):
+    """Convolution = Im2Col + Einsum: forward vs the as_strided+np.einsum restatement of the
+    reference's commented-out design, first- and second-order grads vs the oracle graph."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((3, 9, 8, 3)); w = rng.standard_normal((3, 2, 3, 5)); w2 = rng.standard_normal((2, 2, 5, 4))
+    check(ad.Conv2D(ad.Variable(x, name="x"), ad.Variable(w, name="w"))(), onp.conv_valid_nhwc(x, w))
+    outs = {}
+    for m in (onp, ad):
+        X, W, W2 = m.Variable(x.copy(), name="x"), m.Variable(w.copy(), name="w"), m.Variable(w2.copy(), name="w2")
+        h = m.ReLU(m.Conv2D(X, W))
+        y = m.Tanh(m.Conv2D(h, W2))
+        g = m.grad(y, [X, W, W2])
+        gg = m.grad(g[1], [W])[0]
+        outs[m] = [np.array(y())] + [np.array(t()) for t in g] + [np.array(gg())]
+    for a, b in zip(outs[ad], outs[onp]):
+        check(a, b, tol=1e-11, what="conv")
+    # adjointness: <im2col(x), c> == <x, col2im(c)>
+    c = rng.standard_normal((3 * 7 * 7, 3 * 2 * 3))
+    lhs = float(np.sum(np.asarray(ad.Im2Col(ad.Variable(x, name="x"), 3, 2)()) * c))
+    rhs = float(np.sum(x * np.asarray(ad.Col2Im(ad.Variable(c, name="c"), x.shape, 3, 2)())))
+    assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
+
+
+def test_evaluate_many_and_fusion_toggle(ad):
+    from autodiff_b200.core import engine
+    rng = np.random.default_rng(13)
+    xv = rng.standard_normal((65, 33)); yv = rng.random((65, 33)) + 0.5
+
+    def build():
+        X, Y = ad.Variable(xv, name="x"), ad.Variable(yv, name="y")
+        r = ad.ReLU(X @ ad.Transpose(Y))
+        return [ad.Tanh(r) * 2 + 1, (r * r + r) / (1 + ad.Exp(-r)), ad.Einsum("ab->b", ad.Sigmoid(r) * r)]
+    a = build()
+    engine.evaluate_many(a)
+    l0 = ad.launch_count()
+    fused = [np.array(n()) for n in a]
+    engine.fusion_enabled = False
+    try:
+        unfused = [np.array(n()) for n in build()]
+    finally:
+        engine.fusion_enabled = True
+    for f, u in zip(fused, unfused):
+        check(f, u, tol=1e-15)

@@ -140,6 +140,8 @@ int main(int argc, char** argv) {
             fails += run_case(c2, false, 0);
             Case c3{s[0], s[1], s[2], s[3], a, b, 1, 2};   // odd pitch -> generic kernel
             fails += run_case(c3, false, 0);
+            Case c4{s[0], s[1], s[2], s[3], a, b, 0, 3};   // 64x64 tiles
+            fails += run_case(c4, false, 0);
         }
     }
     printf("correctness: %d failing cases\n", fails);
@@ -153,6 +155,12 @@ int main(int argc, char** argv) {
         run_case(Case{8192, 4096, 4097, 1, 1, 0, 0, 1}, true, 3);   // MLP layer fwd (ragged K)
         run_case(Case{4097, 4096, 8192, 1, 0, 0, 0, 1}, true, 3);   // MLP dW
         run_case(Case{2048, 2048, 2048, 1, 1, 0, 0, 2}, true, 2);   // generic kernel speed
+        run_case(Case{512, 1024, 1024, 1, 1, 0, 0, 3}, true, 3);    // char-rnn h@w, 64x64 tiles
+        run_case(Case{512, 1024, 1024, 1, 1, 0, 0, 4}, true, 3);    // same, 128x128 tiles
+        run_case(Case{512, 1024, 1024, 1, 1, 1, 0, 3}, true, 3);
+        run_case(Case{1024, 1024, 512, 1, 0, 0, 0, 3}, true, 3);    // char-rnn dW
+        run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 3}, true, 3);   // 8-way sharded MLP layer, small tiles
+        run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 4}, true, 3);   // same, big tiles
     }
     return fails ? 1 : 0;
 }
