@@ -18,7 +18,7 @@
 
 namespace adb {
 
-constexpr int EW_RANK = 5;
+constexpr int EW_RANK = 6;
 constexpr int EW_TEMPS = 8;
 
 // q = n / d for n < 2^31 without a divide: d == 1 ? n : umulhi(n, mul) >> shr   (round-up magic number)
@@ -392,7 +392,8 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
     const bool lc = P.dim[0] >= 32 * V;                       // long rows: warp-wide coalesced tiles
     const long long per_item = lc ? 32 * V : V;
     const long long chunks0 = (P.dim[0] + per_item - 1) / per_item;
-    const long long work = chunks0 * P.dim[1] * P.dim[2] * P.dim[3] * P.dim[4];
+    long long work = chunks0;
+    for (int k = 1; k < EW_RANK; ++k) work *= P.dim[k];
     P.nd = nd < 1 ? 1 : nd;
     P.total = (unsigned long long)work;
     bool big = work >= (1LL << 31);

@@ -24,6 +24,7 @@
 #include <cudaTypedefs.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "adb_internal.h"
 
@@ -93,8 +94,10 @@ __device__ __forceinline__ double2 lds128(const unsigned char* p) { return *rein
 struct GemmParams {
     int M, N, K;
     int tiles_m, tiles_n;
+    int kt_per_split;            // k-tiles each blockIdx.z handles (split-K); == all k-tiles when gridDim.z == 1
+    int _pad;
     double* C;
-    long long c_sm, c_sn, c_sb;
+    long long c_sm, c_sn, c_sb, c_ss;   // c_ss: stride between split-K partial results
 };
 
 // ----------------------------------------------------------------------------- TMA + DMMA kernel
@@ -123,7 +126,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tn = (tile % group_size) / gm;
     const int m0 = tm * BM, n0 = tn * BN;
     const int batch = blockIdx.y;
-    const int num_kt = (p.K + BK - 1) / BK;
+    const int total_kt = (p.K + BK - 1) / BK;
+    const int kt_first = blockIdx.z * p.kt_per_split;            // split-K: this CTA's slice of the k-tiles
+    const int num_kt = min(p.kt_per_split, total_kt - kt_first);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -144,7 +149,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_expect_tx(fb, STAGE_BYTES);
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + A_TILE_BYTES;
-        const int k0 = kt * BK;
+        const int k0 = (kt_first + kt) * BK;
         if (A_KC) {
             tma_load_3d(sa, &tmA, fb, k0, m0, batch);
         } else {
@@ -247,7 +252,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 
     // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
-    double* __restrict__ Cb = p.C + (long long)batch * p.c_sb;
+    double* __restrict__ Cb = p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int row = m0 + warp_m * (BM / 2) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
@@ -376,7 +381,7 @@ static bool tma_ok(const double* base, long long s_other, long long s_batch, lon
 }
 
 template <class Cfg, bool A_KC, bool B_KC>
-static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, cudaStream_t st) {
+static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, int splits, cudaStream_t st) {
     static bool attr_set = false;
     auto kern = gemm_tma_kernel<Cfg, A_KC, B_KC>;
     constexpr int GEMM_SMEM = Cfg::SMEM;
@@ -385,7 +390,7 @@ static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
         if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, 1);
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("gemm_tma launch failed: %s", cudaGetErrorString(e));
@@ -457,10 +462,31 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         CUtensorMap ta, tb;
         bool ok;
         const long long a_bs = batch > 1 ? d->a_sb : 2, b_bs = batch > 1 ? d->b_sb : 2;
-        // fewer than one wave of 128x128 tiles: quarter-size tiles keep more SMs busy
+        // Tile choice: 128x128 tiles unless wave quantisation on 148 SMs would idle > 5% of the machine, then 64x64
+        // (2 CTAs/SM, 4x finer granularity).  Split-K when even the small tiles cannot fill the SMs and K is long
+        // (weight-gradient GEMMs of conv / rnn layers: tiny M x N, huge K).
         const long long big_tiles = ((M + 127) / 128) * ((N + 127) / 128) * batch;
-        const bool small = force_path == 3 || (force_path != 4 && big_tiles < 148);
+        const double waste_big = (double)((big_tiles + 147) / 148 * 148) / (double)big_tiles;
+        const bool small = force_path == 3 || (force_path != 4 && waste_big > 1.05);
         const int bm = small ? CfgSmall::BM : CfgBig::BM, bn = small ? CfgSmall::BN : CfgBig::BN;
+        const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
+        const long long slots = small ? 296 : 148;
+        const int total_kt = (int)((K + BK - 1) / BK);
+        int splits = 1;
+        if (tiles * 2 <= slots && total_kt >= 32) {
+            long long s1 = slots / tiles;
+            if (s1 > total_kt / 16) s1 = total_kt / 16;
+            if (s1 > 128) s1 = 128;
+            if (s1 > 1) splits = (int)s1;
+        }
+        int kt_per_split = (total_kt + splits - 1) / splits;
+        splits = (total_kt + kt_per_split - 1) / kt_per_split;
+        double* ws_c = nullptr;
+        const long long Np = (N + 1) & ~1LL;
+        if (splits > 1) {
+            cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws_c), (size_t)splits * batch * M * Np * sizeof(double), st);
+            if (e != cudaSuccess) return set_error("gemm: split-K workspace allocation failed: %s", cudaGetErrorString(e));
+        }
         if (a_kc) ok = make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, bm);
         else      ok = make_tmap(&ta, d->A, M, K, batch, d->a_sk, a_bs, 16, BK);
         if (ok) {
@@ -472,18 +498,37 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             p.M = (int)M; p.N = (int)N; p.K = (int)K;
             p.tiles_m = (int)((M + bm - 1) / bm);
             p.tiles_n = (int)((N + bn - 1) / bn);
-            p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb;
+            p.kt_per_split = kt_per_split; p._pad = 0;
+            if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
+            else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
+            int rc;
             if (small) {
-                if (a_kc && b_kc) return launch_tma<CfgSmall, true, true>(ta, tb, p, (int)batch, st);
-                if (a_kc && !b_kc) return launch_tma<CfgSmall, true, false>(ta, tb, p, (int)batch, st);
-                if (!a_kc && b_kc) return launch_tma<CfgSmall, false, true>(ta, tb, p, (int)batch, st);
-                return launch_tma<CfgSmall, false, false>(ta, tb, p, (int)batch, st);
+                if (a_kc && b_kc) rc = launch_tma<CfgSmall, true, true>(ta, tb, p, (int)batch, splits, st);
+                else if (a_kc && !b_kc) rc = launch_tma<CfgSmall, true, false>(ta, tb, p, (int)batch, splits, st);
+                else if (!a_kc && b_kc) rc = launch_tma<CfgSmall, false, true>(ta, tb, p, (int)batch, splits, st);
+                else rc = launch_tma<CfgSmall, false, false>(ta, tb, p, (int)batch, splits, st);
+            } else {
+                if (a_kc && b_kc) rc = launch_tma<CfgBig, true, true>(ta, tb, p, (int)batch, splits, st);
+                else if (a_kc && !b_kc) rc = launch_tma<CfgBig, true, false>(ta, tb, p, (int)batch, splits, st);
+                else if (!a_kc && b_kc) rc = launch_tma<CfgBig, false, true>(ta, tb, p, (int)batch, splits, st);
+                else rc = launch_tma<CfgBig, false, false>(ta, tb, p, (int)batch, splits, st);
             }
-            if (a_kc && b_kc) return launch_tma<CfgBig, true, true>(ta, tb, p, (int)batch, st);
-            if (a_kc && !b_kc) return launch_tma<CfgBig, true, false>(ta, tb, p, (int)batch, st);
-            if (!a_kc && b_kc) return launch_tma<CfgBig, false, true>(ta, tb, p, (int)batch, st);
-            return launch_tma<CfgBig, false, false>(ta, tb, p, (int)batch, st);
+            if (rc == 0 && splits > 1) {
+                // C[b][m][n] = sum_z ws[z][b][m][n]  (deterministic order, column-mode reduction kernel)
+                ReduceSpec S;
+                memset(&S, 0, sizeof S);
+                S.n_ops = 1; S.n_o = 3; S.n_r = 1; S.group = 1;
+                S.odim[0] = N; S.odim[1] = M; S.odim[2] = batch;
+                S.out_s[0] = d->c_sn; S.out_s[1] = d->c_sm; S.out_s[2] = d->c_sb;
+                S.op_os[0][0] = 1; S.op_os[0][1] = Np; S.op_os[0][2] = M * Np;
+                S.rdim[0] = splits; S.op_rs[0][0] = (long long)batch * M * Np;
+                S.op[0] = ws_c; S.out = d->C;
+                rc = reduce_run(S, st);
+            }
+            if (ws_c) cudaFreeAsync(ws_c, st);
+            return rc;
         }
+        if (ws_c) cudaFreeAsync(ws_c, st);
         if (force_path == 1 || force_path >= 3) return set_error("gemm: cuTensorMapEncodeTiled rejected the operands");
     }
     // generic path

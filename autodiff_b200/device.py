@@ -103,7 +103,8 @@ class DeviceArray:
         shape = tuple(int(s) for s in shape)
         t = torch()
         if len(shape) >= 2:
-            pitch = shape[-1] + (shape[-1] & 1)
+            # short innermost extents (channels of an NHWC image) are never TMA rows: keep them dense
+            pitch = shape[-1] + (shape[-1] & 1) if shape[-1] >= 16 else shape[-1]
             n = pitch
             for s in shape[:-1]:
                 n *= s

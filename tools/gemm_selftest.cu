@@ -144,6 +144,11 @@ int main(int argc, char** argv) {
             fails += run_case(c4, false, 0);
         }
     }
+    // split-K (auto path): tiny M x N, long K
+    for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) {
+        long long sk[][4] = {{400, 32, 50000, 1}, {100, 70, 20000, 2}, {64, 64, 8192, 1}, {33, 17, 4097, 3}};
+        for (auto& s : sk) fails += run_case(Case{s[0], s[1], s[2], s[3], a, b, 0, 0}, false, 0);
+    }
     printf("correctness: %d failing cases\n", fails);
     if (!quick) {
         for (long long n : {2048ll, 4096ll, 8192ll}) {
@@ -161,6 +166,10 @@ int main(int argc, char** argv) {
         run_case(Case{1024, 1024, 512, 1, 0, 0, 0, 3}, true, 3);    // char-rnn dW
         run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 3}, true, 3);   // 8-way sharded MLP layer, small tiles
         run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 4}, true, 3);   // same, big tiles
+        run_case(Case{8192, 8192, 8192, 1, 1, 0, 0, 3}, true, 2);   // small tiles at full size (peak efficiency of the 64x64 config)
+        run_case(Case{4097, 4096, 8192, 1, 0, 0, 0, 0}, true, 3);   // MLP dW, auto tile choice
+        run_case(Case{400, 32, 802816, 1, 0, 0, 0, 0}, true, 3);    // conv dW: split-K
+        run_case(Case{1024, 1024, 512, 1, 0, 0, 0, 0}, true, 3);    // char-rnn dW auto
     }
     return fails ? 1 : 0;
 }
