@@ -24,6 +24,7 @@
 #include <cudaTypedefs.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "adb_internal.h"
@@ -467,7 +468,12 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         // (weight-gradient GEMMs of conv / rnn layers: tiny M x N, huge K).
         const long long big_tiles = ((M + 127) / 128) * ((N + 127) / 128) * batch;
         const double waste_big = (double)((big_tiles + 147) / 148 * 148) / (double)big_tiles;
-        const bool small = force_path == 3 || (force_path != 4 && waste_big > 1.05);
+        static int tile_pref = -1;     // ADB_GEMM_TILE=small|big overrides the heuristic (experiments)
+        if (tile_pref < 0) {
+            const char* e = getenv("ADB_GEMM_TILE");
+            tile_pref = !e ? 0 : (!strcmp(e, "small") ? 1 : (!strcmp(e, "big") ? 2 : 0));
+        }
+        const bool small = force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && waste_big > 1.05)));
         const int bm = small ? CfgSmall::BM : CfgBig::BM, bn = small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
         const long long slots = small ? 296 : 148;

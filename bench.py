@@ -253,6 +253,14 @@ def run_gpu(args):
         except Exception as ex:      # reported, never silently dropped
             mlp = {"error": repr(ex)[:300]}
 
+    extra = None
+    if rank == 0 and world == 1 and not args.skip_mlp:
+        try:
+            from autodiff_b200 import workloads as wl
+            extra = {"c4_conv_b256": wl.bench_conv(ad), "c5_char_rnn_h1024_t128_b512_second_order": wl.bench_char_rnn(ad)}
+        except Exception as ex:
+            extra = {"error": repr(ex)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = run_reference_sample(reps=1)
@@ -266,7 +274,7 @@ def run_gpu(args):
                            "flop_per_step": flops, "l2": "inputs (512 MiB - 2 GiB each) exceed the 126 MB L2",
                            "parallelism": "replicas x%d (the sweep has no exchange step)" % world},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches) * world,
-                "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "mlp_train": mlp}
+                "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "mlp_train": mlp, "other_configs": extra}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
