@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadb200.so")
-SOURCES = ["adb_core.cu", "gemm_f64.cu", "ewise.cu", "reduce.cu", "einsum.cu", "conv.cu"]
+SOURCES = ["adb_core.cu", "gemm_f64.cu", "gemm_tf32x3.cu", "ewise.cu", "reduce.cu", "einsum.cu", "conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -17,6 +17,7 @@ int set_error(const char* fmt, ...) {
     return 1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int g_precision = 0;
 }  // namespace adb
 
 extern "C" {
@@ -47,6 +48,13 @@ int adb_init(int device) {
     cudaGetLastError();
     return 0;
 }
+
+int adb_set_precision(int precision) {
+    if (precision != 0 && precision != 1) return adb::set_error("adb_set_precision: unknown precision %d", precision);
+    adb::g_precision = precision;
+    return 0;
+}
+int adb_get_precision(void) { return adb::g_precision; }
 
 int adb_sync(void* stream) {
     ADB_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));

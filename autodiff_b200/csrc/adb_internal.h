@@ -9,6 +9,8 @@ namespace adb {
 int set_error(const char* fmt, ...);   // stores a thread-local message, returns 1
 void count_launch(int n = 1);
 int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path);
+int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st);
+extern int g_precision;   // 0 = FP64 DMMA, 1 = 3xTF32 tcgen05
 int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out, const adb_tensor* outs,
               cudaStream_t st);
 struct ReduceSpec {           // dims innermost-first, already collapsed (see reduce.cu)

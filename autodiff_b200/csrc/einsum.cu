@@ -305,6 +305,8 @@ static int run_problem(const Problem& P, cudaStream_t st, std::string* desc) {
             *desc = b;
             return 0;
         }
+        // the 3xTF32 tcgen05 variant only pays off (and only has tiles) for reasonably large contractions
+        if (g_precision == 1 && d.M >= 64 && d.N >= 64 && d.K >= 32) return gemm_tf32x3(&d, st);
         return gemm_f64(&d, st, 0);
     }
     return run_reduce(P, st, desc);

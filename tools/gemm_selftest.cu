@@ -126,9 +126,63 @@ static int run_case(const Case& c, bool time_it, int reps) {
     return bad;
 }
 
+// ---- 3xTF32 tcgen05 variant: same contract, tolerance 1e-4 (north_star), expected ~1e-7
+static int run_tf32(long long M, long long N, long long K, long long nb, int a_kc, int b_kc, bool time_it) {
+    adb_gemm_desc d; memset(&d, 0, sizeof d);
+    d.M = M; d.N = N; d.K = K; d.batch = nb;
+    long long a_ld = a_kc ? K + 1 : M + 3, b_ld = b_kc ? K + 1 : N + 3, c_ld = N + 1;   // odd pitches on purpose: any strides are legal
+    long long a_elems = (a_kc ? M : K) * a_ld, b_elems = (b_kc ? N : K) * b_ld;
+    if (a_kc) { d.a_sm = a_ld; d.a_sk = 1; } else { d.a_sm = 1; d.a_sk = a_ld; }
+    if (b_kc) { d.b_sn = b_ld; d.b_sk = 1; } else { d.b_sn = 1; d.b_sk = b_ld; }
+    d.a_sb = a_elems; d.b_sb = b_elems; d.c_sm = c_ld; d.c_sn = 1; d.c_sb = M * c_ld;
+    double *A, *B, *C, *R, *res;
+    CK(cudaMalloc(&A, a_elems * nb * 8)); CK(cudaMalloc(&B, b_elems * nb * 8));
+    CK(cudaMalloc(&C, M * c_ld * nb * 8)); CK(cudaMalloc(&R, M * c_ld * nb * 8)); CK(cudaMalloc(&res, 16));
+    fill_rand<<<1024, 256>>>(A, a_elems * nb, 11); fill_rand<<<1024, 256>>>(B, b_elems * nb, 12);
+    CK(cudaMemset(C, 0, M * c_ld * nb * 8)); CK(cudaMemset(R, 0, M * c_ld * nb * 8)); CK(cudaMemset(res, 0, 16));
+    d.A = A; d.B = B; d.C = C;
+    int rc = adb_gemm_tf32x3(&d, 0);
+    if (rc) { printf("FAIL tf32x3 launch: %s\n", adb_last_error()); return 1; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("FAIL tf32x3 kernel error: %s\n", cudaGetErrorString(e)); exit(3); }
+    int bad = 0;
+    if ((double)M * N * K * nb <= 4e11) {
+        adb_gemm_desc r = d; r.C = R;
+        dim3 grid((unsigned)((N + 127) / 128), (unsigned)M, (unsigned)nb);
+        naive_gemm<<<grid, 128>>>(r);
+        max_diff<<<1024, 256>>>(C, R, (size_t)M * c_ld * nb, res);
+        double h[2]; CK(cudaMemcpy(h, res, 16, cudaMemcpyDeviceToHost));
+        double rel = h[0] / (h[1] > 0 ? h[1] : 1);
+        bad = !(rel < 1e-5);
+        printf("%s tf32x3 M=%lld N=%lld K=%lld b=%lld A=%s B=%s relerr=%.3e (bar 1e-4)\n", bad ? "FAIL" : "ok  ", M, N, K, nb,
+               a_kc ? "KC" : "MC", b_kc ? "KC" : "MC", rel);
+    }
+    if (time_it) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float best = 1e30f;
+        for (int r = 0; r < 3; ++r) {
+            cudaEventRecord(e0); adb_gemm_tf32x3(&d, 0); cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        printf("     time tf32x3 (incl. fp64->hi/lo split) M=%lld N=%lld K=%lld b=%lld : %.3f ms  %.2f TFLOP/s effective\n", M, N, K, nb, best,
+               2.0 * M * N * K * nb / best * 1e-9);
+    }
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(R); cudaFree(res);
+    return bad;
+}
+
 int main(int argc, char** argv) {
     bool quick = argc > 1 && !strcmp(argv[1], "quick");
     if (adb_init(0)) { printf("adb_init failed: %s\n", adb_last_error()); return 1; }
+    if (argc > 1 && !strcmp(argv[1], "tf32")) {
+        int fails = 0;
+        long long shapes[][4] = {{128, 128, 32, 1}, {128, 128, 256, 1}, {256, 384, 100, 1}, {200, 136, 77, 1}, {257, 129, 50, 3}, {1000, 520, 333, 2}, {64, 64, 1024, 1}};
+        for (auto& s : shapes) for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) fails += run_tf32(s[0], s[1], s[2], s[3], a, b, false);
+        printf("tf32x3 correctness: %d failing cases\n", fails);
+        for (long long n : {2048ll, 4096ll, 8192ll}) run_tf32(n, n, n, 1, 1, 0, true);
+        run_tf32(1024, 1024, 1024, 64, 1, 0, true);
+        return fails ? 1 : 0;
+    }
     int fails = 0;
     for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) {
         long long shapes[][4] = {{128, 128, 16, 1}, {128, 128, 96, 1}, {64, 40, 24, 1}, {200, 136, 100, 1}, {257, 129, 50, 3},
