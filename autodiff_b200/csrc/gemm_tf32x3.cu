@@ -95,8 +95,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 struct Params {
     int M, N, K;
     int tiles_m, tiles_n;
+    int kb_per_split, _pad;          // k-blocks per blockIdx.z (K is chunked so fp32 accumulation chains stay short)
     double* C;
-    long long c_sm, c_sn, c_sb;
+    long long c_sm, c_sn, c_sb, c_ss;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -116,7 +117,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
     const int m0 = tm * BM, n0 = tn * BN;
     const int batch = blockIdx.y;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int total_kb = (p.K + BK - 1) / BK;
+    const int kb_first = blockIdx.z * p.kb_per_split;
+    const int num_kb = min(p.kb_per_split, total_kb - kb_first);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -146,7 +149,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, STAGE_BYTES);
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const int k0 = kb * BK;
+                const int k0 = (kb_first + kb) * BK;
                 tma_load_3d(st, &tmAh, fb, k0, m0, batch);
                 tma_load_3d(st + TILE_BYTES, &tmAl, fb, k0, m0, batch);
                 tma_load_3d(st + 2 * TILE_BYTES, &tmBh, fb, k0, n0, batch);
@@ -182,7 +185,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + quad * 32 + lane;
-        double* crow = p.C + (long long)batch * p.c_sb + (long long)row * p.c_sm;
+        double* crow = p.C + (long long)blockIdx.z * p.c_ss + (long long)batch * p.c_sb + (long long)row * p.c_sm;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
@@ -296,17 +299,46 @@ int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
         if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm_tf32x3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
         attr_set = true;
     }
+    // The tensor core accumulates in fp32 with truncation, so the error of one accumulation chain grows ~linearly
+    // with its length (measured 1.4e-5 at K = 2048, 3.3e-5 at 4096).  K is therefore processed in chunks of <= 2048
+    // by separate CTAs (blockIdx.z) whose fp64 partial tiles are summed in fp64 by the reduction kernel.
+    const int total_kb = (int)((K + BK - 1) / BK);
+    const int max_kb = 2048 / BK;
+    int splits = (total_kb + max_kb - 1) / max_kb;
+    const int kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kb_per_split - 1) / kb_per_split;
+    double* ws_c = nullptr;
+    const long long Np = (N + 1) & ~1LL;
+    if (splits > 1) {
+        e = cudaMallocAsync(reinterpret_cast<void**>(&ws_c), (size_t)splits * batch * M * Np * sizeof(double), st);
+        if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm_tf32x3: split workspace allocation failed: %s", cudaGetErrorString(e)); }
+    }
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
-    p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb;
-    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, 1);
+    p.kb_per_split = kb_per_split; p._pad = 0;
+    if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
+    else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
     gemm_tf32x3_kernel<<<grid, THREADS, SMEM, st>>>(tAh, tAl, tBh, tBl, p);
     e = cudaGetLastError();
     cudaFreeAsync(ws, st);
-    if (e != cudaSuccess) return set_error("gemm_tf32x3 launch failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { if (ws_c) cudaFreeAsync(ws_c, st); return set_error("gemm_tf32x3 launch failed: %s", cudaGetErrorString(e)); }
     count_launch();
-    return 0;
+    int rc = 0;
+    if (splits > 1) {
+        ReduceSpec S;
+        memset(&S, 0, sizeof S);
+        S.n_ops = 1; S.n_o = 3; S.n_r = 1; S.group = 1;
+        S.odim[0] = N; S.odim[1] = M; S.odim[2] = batch;
+        S.out_s[0] = d->c_sn; S.out_s[1] = d->c_sm; S.out_s[2] = d->c_sb;
+        S.op_os[0][0] = 1; S.op_os[0][1] = Np; S.op_os[0][2] = M * Np;
+        S.rdim[0] = splits; S.op_rs[0][0] = (long long)batch * M * Np;
+        S.op[0] = ws_c; S.out = d->C;
+        rc = reduce_run(S, st);
+        cudaFreeAsync(ws_c, st);
+    }
+    return rc;
 }
 
 }  // namespace adb
