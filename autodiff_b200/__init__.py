@@ -12,4 +12,4 @@ from .core.high_level_ops import * # noqa: F401,F403
 from .core.wrappers import checkpoint
 from .core.conv import Col2Im, Conv2D, Im2Col
 from .core.grad import grad
-from .device import DeviceArray, init, launch_count, pinned_empty, precision, set_precision, synchronize, to_device, to_host, use_stream
+from .device import DeviceArray, ewise_stats, force_interpreter, init, launch_count, pinned_empty, precision, set_precision, synchronize, to_device, to_host, use_stream

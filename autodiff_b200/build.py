@@ -6,7 +6,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadb200.so")
-SOURCES = ["adb_core.cu", "gemm_f64.cu", "gemm_tf32x3.cu", "ewise.cu", "reduce.cu", "einsum.cu", "conv.cu"]
+EW_NSHARDS = 4   # must match N_SHARDS in tools/gen_ewise_catalog.py
+# (source, extra nvcc flags, object name)
+SOURCES = [(f, [], f.replace(".cu", ".o")) for f in
+           ["adb_core.cu", "gemm_f64.cu", "gemm_tf32x3.cu", "ewise.cu", "reduce.cu", "einsum.cu", "conv.cu"]]
+SOURCES += [("ewise_catalog.cu", ["-DEW_SHARD=%d" % k], "ewise_catalog_%d.o" % k) for k in range(EW_NSHARDS)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -26,13 +30,13 @@ def build_lib(force=False, verbose=False):
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+    for src, extra, objname in SOURCES:
+        obj = os.path.join(HERE, "build", objname)
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((objname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:

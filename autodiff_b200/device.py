@@ -96,15 +96,15 @@ class DeviceArray:
     # ---- construction
     @staticmethod
     def empty(shape):
-        """Row pitch of >=2-D arrays is padded to an even element count so every row is 16-byte aligned
-        (TMA global strides must be multiples of 16 B; the NN bias trick makes odd widths like 4097 common,
-        reference high_level_ops.py:32-35)."""
+        """Row pitch of >=2-D arrays is padded to a multiple of 4 elements so every row is 32-byte aligned
+        (TMA global strides must be multiples of 16 B, the elementwise kernels use 256-bit accesses; the NN bias
+        trick makes odd widths like 4097 common, reference high_level_ops.py:32-35)."""
         _ensure_init()
         shape = tuple(int(s) for s in shape)
         t = torch()
         if len(shape) >= 2:
             # short innermost extents (channels of an NHWC image) are never TMA rows: keep them dense
-            pitch = shape[-1] + (shape[-1] & 1) if shape[-1] >= 16 else shape[-1]
+            pitch = shape[-1] + (-shape[-1] % 4) if shape[-1] >= 16 else shape[-1]
             n = pitch
             for s in shape[:-1]:
                 n *= s
@@ -369,3 +369,19 @@ class precision:
 
 def set_precision(mode):
     _lib.check(_lib.lib().adb_set_precision(precision.MODES[mode]))
+
+
+# --------------------------------------------------------------------------------------- diagnostics
+def ewise_stats():
+    """One line per distinct elementwise program run so far: "<calls> <quads> <static|interp> op:arg ..."
+    (input of tools/gen_ewise_catalog.py --merge)."""
+    L = _lib.lib()
+    n = L.adb_ewise_stats(None, 0)
+    buf = C.create_string_buffer(n + 16)
+    L.adb_ewise_stats(buf, n + 16)
+    return buf.value.decode()
+
+
+def force_interpreter(on=True):
+    """Runs every elementwise program on the bytecode interpreter (A/B against the catalogued kernels)."""
+    _lib.check(_lib.lib().adb_ewise_force_interpreter(1 if on else 0))

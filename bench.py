@@ -276,6 +276,8 @@ def run_gpu(args):
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches) * world,
                 "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "mlp_train": mlp, "other_configs": extra}
         print(json.dumps(line))
+        if os.environ.get("ADB_EW_STATS"):        # which elementwise programs ran (input of tools/gen_ewise_catalog.py)
+            open(os.environ["ADB_EW_STATS"], "w").write(ad.ewise_stats())
     if dist is not None:
         dist.destroy_process_group()
 

@@ -119,6 +119,13 @@ typedef struct adb_ew_instr {
 ADB_API int adb_ewise(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out,
               const adb_tensor* outs, void* stream);
 
+/* Diagnostics for the program dispatcher: programs listed in csrc/ewise_catalog.txt are compiled to straight-line
+ * kernels, everything else runs on the bytecode interpreter.  adb_ewise_stats writes one line per distinct program
+ * seen so far ("<calls> <quads> <static|interp> op:arg ...") and returns the buffer size needed;
+ * adb_ewise_force_interpreter(1) disables the catalogue (A/B measurements, parity tests of both paths). */
+ADB_API int adb_ewise_stats(char* buf, size_t buflen);
+ADB_API int adb_ewise_force_interpreter(int on);
+
 /* ---- einsum: replaces np.einsum(self.op_str, *arr) at reference autodiff/core/ops.py:180 ----------
  *  op_str uses single letters [a-zA-Z] with an explicit "->" (the host expands "..." first, mirroring
  *  ops.py:131,167-170).  The planner canonicalises the subscripts into one of: alias-free copy/permute,

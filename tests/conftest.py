@@ -28,3 +28,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """ADB_EW_STATS=<file>: dump which elementwise programs the GPU tests ran (tools/gen_ewise_catalog.py --merge)."""
+    import os
+    path = os.environ.get("ADB_EW_STATS")
+    if path:
+        try:
+            import autodiff_b200 as ad
+            open(path, "w").write(ad.ewise_stats())
+        except Exception:
+            pass

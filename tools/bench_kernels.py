@@ -108,3 +108,4 @@ for (M, N, K, tag) in ((8192, 8192, 8192, "C2a"), (8192, 4096, 4097, "C3 fwd"), 
     del a, bb
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(results, open("gpurun_out/kernels.json", "w"), indent=1)
+open("gpurun_out/ewise_stats_kernels.txt", "w").write(ad.ewise_stats())
