@@ -16,6 +16,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+
 #include "adb_internal.h"
 
 namespace adb {
@@ -153,9 +156,14 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(const __grid_const
 }
 
 // ----------------------------------------------------------------------------- fast path (<= 3 output dims, <= 2 summed dims)
-// The summed space is flattened to rho in [0, R0*R1) and decoded with multiply-shift divisors; every lane keeps
-// four independent (optionally 128-bit) loads per operand in flight, so short inner extents (R0 = 128 in the
-// 'ijkl,jl->ik' sweep member) no longer serialise on one load per step.
+// Two streaming kernels, both built from what tools/probe_stream.cu measured on B200: 256-bit loads, four independent
+// loads per operand in flight per lane, one-shot grids, multiply-shift index decoding.
+//   red_row_kernel<G>  : the fastest-varying index of the big operand is SUMMED.  G lanes (a warp or a whole CTA)
+//                        stride along the flattened summed index in quads; shuffle (+ shared memory) combine.
+//   red_col_kernel<WR> : the fastest-varying index is an OUTPUT index.  A lane owns one output quad; the WR warps of a
+//                        CTA take interleaved slices of the summed index and combine through shared memory.
+// Few outputs => the summed range is sliced over gridDim.y; partials go to a workspace and the LAST slice to arrive
+// (self-resetting arrival counter per blockIdx.x) re-adds them in slice order: one launch, deterministic result.
 struct FastDiv32 {
     unsigned mul, shr, d, _pad;
 };
@@ -172,209 +180,428 @@ static FastDiv32 make_fd(unsigned d) {
 }
 __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv32& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
 
-struct Red2Params {
-    int n_ops, square, splits, _pad;
-    unsigned O, R, chunk, _pad2;
-    FastDiv32 odiv[3];
-    FastDiv32 r0div;
+struct Red3Params {
+    int n_ops, square, splits, fin_vec;
+    unsigned NG;          // row: outputs; col: output quads (groups of work that own outputs)
+    unsigned O0;          // extent of the innermost output dim (elements)
+    unsigned R, chunk;    // flattened summed range per output (row: in units of VEC elements) and its per-split length
+    unsigned vecmask;     // bit t: operand t has unit stride along the vector dimension (else it is broadcast along it)
+    unsigned out_vec;     // col: the output can be stored as one 256-bit quad
+    FastDiv32 odiv[3];    // row: output dims; col: [quads of dim 0, dim 1, dim 2]
+    FastDiv32 r0div;      // row: quads (VEC = 4) or elements of summed dim 0; col: elements of summed dim 0
     long long out_s[3];
     long long op_os[ADB_RED_MAX_OPS][3];
     long long op_r0s[ADB_RED_MAX_OPS], op_r1s[ADB_RED_MAX_OPS];
     const double* op[ADB_RED_MAX_OPS];
     double* out;
-    double* partial;
+    double* partial;      // [splits][NG * fin_vec]
+    int* counter;         // one arrival counter per blockIdx.x (self-resetting); the last slice to arrive adds the partials
 };
 
+// Arrival of this CTA's slice: returns true in every thread of the LAST slice to arrive for blockIdx.x, after which
+// the partials of all slices are visible.  The counter is reset so the buffer can be reused by the next launch.
+__device__ __forceinline__ bool red_last_slice(const Red3Params& P) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(P.counter + blockIdx.x, 1);
+        s_last = ticket == P.splits - 1;
+        if (s_last) P.counter[blockIdx.x] = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+struct Quad {
+    double v[4];
+};
+__device__ __forceinline__ Quad ldq(const double* p) {
+    Quad r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
+
+constexpr int RED_U = 4;   // independent loads per operand in flight per lane
+
+// One step of the summed index: fetch every operand's VEC elements (no use of the values here, so that the loads of
+// several steps issue back to back), then fold them into a product.
+template <int NOPS, int VEC, bool COL>
+__device__ __forceinline__ void red_fetch(const Red3Params& P, const double* const (&base)[NOPS], unsigned rho, unsigned nvalid,
+                                          double (&x)[NOPS][VEC]) {
+    const unsigned r1 = fd_div(rho, P.r0div);
+    const unsigned r0 = (rho - r1 * P.r0div.d) * (COL ? 1u : (unsigned)VEC);
+#pragma unroll
+    for (int t = 0; t < NOPS; ++t) {
+        const double* p = base[t] + (long long)r0 * P.op_r0s[t] + (long long)r1 * P.op_r1s[t];
+        if (VEC == 4) {
+            if (!((P.vecmask >> t) & 1u)) { const double sc = __ldg(p); _Pragma("unroll") for (int e = 0; e < VEC; ++e) x[t][e] = sc; }
+            else if (!COL || nvalid == 4) { const Quad q = ldq(p); x[t][0] = q.v[0]; x[t][1 % VEC] = q.v[1]; x[t][2 % VEC] = q.v[2]; x[t][3 % VEC] = q.v[3]; }
+            else { _Pragma("unroll") for (int e = 0; e < VEC; ++e) x[t][e] = e < (int)nvalid ? __ldg(p + e) : 0.0; }
+        } else {
+            x[t][0] = __ldg(p);
+        }
+    }
+}
+template <int NOPS, int VEC>
+__device__ __forceinline__ void red_fold(const Red3Params& P, const double (&x)[NOPS][VEC], double (&acc)[VEC]) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        double v = (NOPS == 1 && P.square) ? x[0][e] * x[0][e] : x[0][e];
+#pragma unroll
+        for (int t = 1; t < NOPS; ++t) v *= x[t][e];
+        acc[e] += v;
+    }
+}
+// Walks rho = first, first + stride, ... < hi : full trips of RED_U steps without bounds checks (straight-line code,
+// all loads of a trip in flight together), then the remainder one step at a time.
+template <int NOPS, int VEC, bool COL>
+__device__ __forceinline__ void red_walk(const Red3Params& P, const double* const (&base)[NOPS], unsigned first, unsigned stride, unsigned hi,
+                                         unsigned nvalid, double (&acc)[VEC]) {
+    unsigned r = first;
+    for (; r + (RED_U - 1) * stride < hi; r += RED_U * stride) {
+        double x[RED_U][NOPS][VEC];
+#pragma unroll
+        for (int u = 0; u < RED_U; ++u) red_fetch<NOPS, VEC, COL>(P, base, r + u * stride, nvalid, x[u]);
+#pragma unroll
+        for (int u = 0; u < RED_U; ++u) red_fold<NOPS, VEC>(P, x[u], acc);
+    }
+    for (; r < hi; r += stride) {
+        double x[NOPS][VEC];
+        red_fetch<NOPS, VEC, COL>(P, base, r, nvalid, x);
+        red_fold<NOPS, VEC>(P, x, acc);
+    }
+}
+
 template <int G, int NOPS, int VEC>
-__global__ void __launch_bounds__(256) reduce2_kernel(const __grid_constant__ Red2Params P) {
+__global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Red3Params P) {
     constexpr int GROUPS = 256 / G;
-    constexpr int UNROLL = 4;
-    const int lane = threadIdx.x % G;
+    const unsigned lane = threadIdx.x % G;
+    const unsigned o = blockIdx.x * GROUPS + threadIdx.x / G;
+    const bool live = o < P.NG;
     const unsigned z = blockIdx.y;
     const unsigned lo = z * P.chunk;
     const unsigned hi = (lo + P.chunk < P.R) ? lo + P.chunk : P.R;
-    __shared__ double warp_part[8];
 
-    for (unsigned o = blockIdx.x * GROUPS + threadIdx.x / G; o < P.O; o += gridDim.x * GROUPS) {
-        // decode the output index
-        unsigned rem = o;
-        long long out_off = 0;
-        const double* base[NOPS];
+    unsigned rem = live ? o : 0;
+    long long out_off = 0;
+    const double* base[NOPS];
 #pragma unroll
-        for (int t = 0; t < NOPS; ++t) base[t] = P.op[t];
+    for (int t = 0; t < NOPS; ++t) base[t] = P.op[t];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const unsigned qn = fd_div(rem, P.odiv[k]);
-            const unsigned i = rem - qn * P.odiv[k].d;
-            rem = qn;
-            out_off += (long long)i * P.out_s[k];
+    for (int k = 0; k < 3; ++k) {
+        const unsigned qn = fd_div(rem, P.odiv[k]);
+        const unsigned i = rem - qn * P.odiv[k].d;
+        rem = qn;
+        out_off += (long long)i * P.out_s[k];
 #pragma unroll
-            for (int t = 0; t < NOPS; ++t) base[t] += (long long)i * P.op_os[t][k];
+        for (int t = 0; t < NOPS; ++t) base[t] += (long long)i * P.op_os[t][k];
+    }
+    double acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
+    if (live) red_walk<NOPS, VEC, false>(P, base, lo + lane, G, hi, VEC, acc);
+    double a = acc[0];
+#pragma unroll
+    for (int e = 1; e < VEC; ++e) a += acc[e];
+#pragma unroll
+    for (int off = (G > 32 ? 16 : G / 2); off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off, G > 32 ? 32 : G);
+    if (G == 256) {
+        __shared__ double warp_part[8];
+        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            a = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += warp_part[w];
         }
-        double acc0 = 0.0, acc1 = 0.0;
-        for (unsigned r = lo + lane * VEC; r < hi; r += UNROLL * G * VEC) {
-            double v0[UNROLL], v1[UNROLL];
+    }
+    if (P.splits == 1) {
+        if (lane == 0 && live) P.out[out_off] = a;
+        return;
+    }
+    if (lane == 0 && live) P.partial[(long long)z * P.NG + o] = a;
+    if (!red_last_slice(P)) return;
+    // last slice: every group re-adds its output's partials in slice order (fixed order => deterministic)
+    if (!live) return;
+    double t = 0.0;
+    for (int zz = lane; zz < P.splits; zz += G) t += __ldcg(P.partial + (long long)zz * P.NG + o);
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const unsigned rho = r + u * G * VEC;
-                v0[u] = 0.0; v1[u] = 0.0;
-                if (rho < hi) {
-                    const unsigned r1 = fd_div(rho, P.r0div);
-                    const unsigned r0 = rho - r1 * P.r0div.d;
-                    if (VEC == 2) {
-                        double2 a;
-                        {
-                            const double* p = base[0] + (long long)r0 * P.op_r0s[0] + (long long)r1 * P.op_r1s[0];
-                            if (P.op_r0s[0] == 0) { const double s = __ldg(p); a = make_double2(s, s); }
-                            else a = __ldg(reinterpret_cast<const double2*>(p));
-                        }
-                        if (NOPS == 1 && P.square) { a.x *= a.x; a.y *= a.y; }
+    for (int off = (G > 32 ? 16 : G / 2); off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off, G > 32 ? 32 : G);
+    if (G == 256) {
+        __shared__ double warp_fin[8];
+        if ((threadIdx.x & 31) == 0) warp_fin[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            t = 0.0;
 #pragma unroll
-                        for (int t = 1; t < NOPS; ++t) {
-                            const double* p = base[t] + (long long)r0 * P.op_r0s[t] + (long long)r1 * P.op_r1s[t];
-                            double2 b;
-                            if (P.op_r0s[t] == 0) { const double s = __ldg(p); b = make_double2(s, s); }
-                            else b = __ldg(reinterpret_cast<const double2*>(p));
-                            a.x *= b.x; a.y *= b.y;
-                        }
-                        v0[u] = a.x; v1[u] = a.y;
-                    } else {
-                        double a = __ldg(base[0] + (long long)r0 * P.op_r0s[0] + (long long)r1 * P.op_r1s[0]);
-                        if (NOPS == 1 && P.square) a *= a;
+            for (int w = 0; w < 8; ++w) t += warp_fin[w];
+        }
+    }
+    if (lane == 0) P.out[out_off] = t;
+}
+
+template <int WR, int NOPS, int VEC>
+__global__ void __launch_bounds__(256, (VEC == 4 && NOPS == 2) ? 3 : 1) red_col_kernel(const __grid_constant__ Red3Params P) {
+    constexpr int OQ_PER_CTA = 256 / WR;
+    const unsigned lane = threadIdx.x % OQ_PER_CTA;
+    const unsigned w = threadIdx.x / OQ_PER_CTA;       // slice of the summed index (0 when WR == 1)
+    const unsigned oq = blockIdx.x * OQ_PER_CTA + lane;
+    const bool live = oq < P.NG;
+    const unsigned z = blockIdx.y;
+    const unsigned lo = z * P.chunk;
+    const unsigned hi = (lo + P.chunk < P.R) ? lo + P.chunk : P.R;
+
+    unsigned rem = live ? oq : 0;
+    long long out_off = 0;
+    const double* base[NOPS];
+    unsigned o0 = 0;
 #pragma unroll
-                        for (int t = 1; t < NOPS; ++t) a *= __ldg(base[t] + (long long)r0 * P.op_r0s[t] + (long long)r1 * P.op_r1s[t]);
-                        v0[u] = a;
-                    }
+    for (int t = 0; t < NOPS; ++t) base[t] = P.op[t];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned qn = fd_div(rem, P.odiv[k]);
+        unsigned i = rem - qn * P.odiv[k].d;
+        rem = qn;
+        if (k == 0) { i *= VEC; o0 = i; }
+        out_off += (long long)i * P.out_s[k];
+#pragma unroll
+        for (int t = 0; t < NOPS; ++t) base[t] += (long long)i * P.op_os[t][k];
+    }
+    const unsigned nvalid = live ? ((P.O0 - o0 < (unsigned)VEC) ? P.O0 - o0 : (unsigned)VEC) : 0u;
+    double acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
+    if (live) red_walk<NOPS, VEC, true>(P, base, lo + w, WR, hi, nvalid, acc);
+    if (WR > 1) {
+        __shared__ double part[WR][OQ_PER_CTA][VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) part[w][lane][e] = acc[e];
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                double a = 0.0;
+#pragma unroll
+                for (int ww = 0; ww < WR; ++ww) a += part[ww][lane][e];
+                acc[e] = a;
+            }
+        }
+    }
+    const bool owner = live && w == 0;
+    if (P.splits > 1) {
+        if (owner) {
+            double* q = P.partial + ((long long)z * P.NG + oq) * VEC;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) q[e] = acc[e];
+        }
+        if (!red_last_slice(P)) return;
+        // last slice: the WR warps take interleaved slices of the partials, then combine in warp order (fixed order)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
+        if (live) {
+#pragma unroll 4
+            for (int zz = w; zz < P.splits; zz += WR) {
+                const double* q = P.partial + ((long long)zz * P.NG + oq) * VEC;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += __ldcg(q + e);
+            }
+        }
+        if (WR > 1) {
+            __shared__ double fin[WR][OQ_PER_CTA][VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) fin[w][lane][e] = acc[e];
+            __syncthreads();
+            if (w == 0) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < WR; ++ww) a += fin[ww][lane][e];
+                    acc[e] = a;
                 }
             }
+        }
+    }
+    if (!owner) return;
+    double* q = P.out + out_off;
+    if (VEC == 4 && nvalid == 4 && P.out_vec) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(q), "d"(acc[0]), "d"(acc[1 % VEC]), "d"(acc[2 % VEC]), "d"(acc[3 % VEC]) : "memory");
+    } else {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) { acc0 += v0[u]; if (VEC == 2) acc1 += v1[u]; }
-        }
-        double acc = acc0 + acc1;
-        if (G > 1) {
-#pragma unroll
-            for (int off = (G > 32 ? 16 : G / 2); off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, G > 32 ? 32 : G);
-        }
-        if (G == 256) {
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                acc = 0.0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) acc += warp_part[w];
-            }
-        }
-        if (lane == 0) {
-            if (P.splits == 1) P.out[out_off] = acc;
-            else P.partial[(long long)z * P.O + o] = acc;
-        }
+        for (int e = 0; e < VEC; ++e)
+            if (e < (int)nvalid) q[e * P.out_s[0]] = acc[e];
     }
 }
 
-__global__ void __launch_bounds__(256) reduce2_finalize_kernel(const __grid_constant__ Red2Params P) {
-    for (unsigned o = blockIdx.x * blockDim.x + threadIdx.x; o < P.O; o += gridDim.x * blockDim.x) {
-        unsigned rem = o;
-        long long out_off = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const unsigned qn = fd_div(rem, P.odiv[k]);
-            out_off += (long long)(rem - qn * P.odiv[k].d) * P.out_s[k];
-            rem = qn;
-        }
-        double acc = 0.0;
-        for (int z = 0; z < P.splits; ++z) acc += P.partial[(long long)z * P.O + o];
-        P.out[out_off] = acc;
+typedef void (*Red3Kernel)(const Red3Params);
+template <int NOPS>
+static Red3Kernel red3_kernel(bool row, int width, int vec) {
+    if (row) {
+        if (width == 256) return vec == 4 ? red_row_kernel<256, NOPS, 4> : red_row_kernel<256, NOPS, 1>;
+        return vec == 4 ? red_row_kernel<32, NOPS, 4> : red_row_kernel<32, NOPS, 1>;
     }
+    if (width == 8) return vec == 4 ? red_col_kernel<8, NOPS, 4> : red_col_kernel<8, NOPS, 1>;
+    return vec == 4 ? red_col_kernel<1, NOPS, 4> : red_col_kernel<1, NOPS, 1>;
 }
 
-template <int G, int VEC>
-static void launch_reduce2(const Red2Params& P, dim3 grid, cudaStream_t st) {
-    switch (P.n_ops) {
-        case 1: reduce2_kernel<G, 1, VEC><<<grid, 256, 0, st>>>(P); break;
-        case 2: reduce2_kernel<G, 2, VEC><<<grid, 256, 0, st>>>(P); break;
-        case 3: reduce2_kernel<G, 3, VEC><<<grid, 256, 0, st>>>(P); break;
-        default: reduce2_kernel<G, 4, VEC><<<grid, 256, 0, st>>>(P); break;
-    }
+// CTA slots of the device for a kernel (SMs x resident CTAs per SM), cached per kernel.
+static long long red3_slots(Red3Kernel k) {
+    static std::map<Red3Kernel, long long> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) return it->second;
+    int occ = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 2; }
+    const long long v = (long long)sms * occ;
+    cache[k] = v;
+    return v;
 }
+
+// Partial-sum workspace: one grow-only buffer per stream (launches on one stream are ordered, so consecutive
+// reductions can reuse it without stream-ordered malloc/free calls between the kernels).
+static double* red3_workspace(cudaStream_t st, size_t bytes) {
+    struct Ws { double* p = nullptr; size_t n = 0; };
+    static std::map<cudaStream_t, Ws> ws;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    Ws& w = ws[st];
+    if (w.n < bytes) {
+        if (w.p) { cudaStreamSynchronize(st); cudaFree(w.p); w.p = nullptr; w.n = 0; }
+        size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes + bytes / 2;
+        if (cudaMalloc(reinterpret_cast<void**>(&w.p), want) != cudaSuccess) { cudaGetLastError(); w.p = nullptr; return nullptr; }
+        w.n = want;
+    }
+    return w.p;
+}
+
+// Self-resetting arrival counters: a ring, so that launches in flight on different streams never share a segment.
+static int* red3_counters(long long n) {
+    constexpr long long RING = 1 << 20;
+    static int* ring = nullptr;
+    static long long head = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (n > RING) return nullptr;
+    if (!ring) {
+        if (cudaMalloc(reinterpret_cast<void**>(&ring), RING * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(ring, 0, RING * sizeof(int));
+    }
+    if (head + n > RING) head = 0;
+    int* p = ring + head;
+    head += n;
+    return p;
+}
+
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 
 // Returns 0 = ran, -1 = not applicable (caller falls back to the generic kernel), >0 = error.
-static int reduce2_try(const ReduceSpec& S, cudaStream_t st) {
-    if (S.n_o > 3 || S.n_r > 2) return -1;
+static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
+    if (S.n_o > 3 || S.n_r > 2 || S.n_r < 1) return -1;
     long long O = 1, R = 1;
     for (int k = 0; k < S.n_o; ++k) O *= S.odim[k];
     for (int k = 0; k < S.n_r; ++k) R *= S.rdim[k];
     if (O <= 0) return 0;
     if (O >= (1LL << 31) || R >= (1LL << 31) || R <= 0) return -1;
-    Red2Params P;
+    const bool row = S.group > 1;
+    if (row && R < 128) return -1;                    // short rows, many outputs: the sub-warp groups of reduce_kernel fit better
+    const long long R0 = S.rdim[0], O0 = S.n_o > 0 ? S.odim[0] : 1;
+
+    Red3Params P;
     memset(&P, 0, sizeof P);
     P.n_ops = S.n_ops; P.square = S.square;
-    P.O = (unsigned)O; P.R = (unsigned)R;
-    for (int k = 0; k < 3; ++k) {
-        P.odiv[k] = make_fd(k < S.n_o ? (unsigned)S.odim[k] : 1u);
-        P.out_s[k] = k < S.n_o ? S.out_s[k] : 0;
-        for (int t = 0; t < S.n_ops; ++t) P.op_os[t][k] = k < S.n_o ? S.op_os[t][k] : 0;
-    }
-    const long long R0 = S.n_r > 0 ? S.rdim[0] : 1;
-    P.r0div = make_fd((unsigned)R0);
     for (int t = 0; t < S.n_ops; ++t) {
-        P.op_r0s[t] = S.n_r > 0 ? S.op_rs[t][0] : 0;
-        P.op_r1s[t] = S.n_r > 1 ? S.op_rs[t][1] : 0;
         P.op[t] = S.op[t];
+        P.op_r0s[t] = S.op_rs[t][0];
+        P.op_r1s[t] = S.n_r > 1 ? S.op_rs[t][1] : 0;
+        for (int k = 0; k < 3; ++k) P.op_os[t][k] = k < S.n_o ? S.op_os[t][k] : 0;
     }
+    for (int k = 0; k < 3; ++k) P.out_s[k] = k < S.n_o ? S.out_s[k] : 0;
     P.out = S.out;
-    const bool row = S.group > 1;
-    int G = 1;
-    if (row) G = (O < 2 * 148) ? 256 : 32;
-    if (!row && O < 4 * 148) G = (O < 64) ? 256 : 32;     // few outputs: cooperate on each even if strided
-    // 128-bit loads along the flattened summed index
-    int VEC = 1;
-    if (G > 1 && (R0 % 2) == 0) {
-        VEC = 2;
-        for (int t = 0; t < S.n_ops && VEC == 2; ++t) {
-            if (P.op_r0s[t] != 0 && P.op_r0s[t] != 1) VEC = 1;
-            if (P.op_r1s[t] & 1) VEC = 1;
-            for (int k = 0; k < 3; ++k) if (P.op_os[t][k] & 1) VEC = 1;
-            if (reinterpret_cast<uintptr_t>(P.op[t]) & 15) VEC = 1;
-        }
+    P.O0 = (unsigned)O0;
+
+    // 256-bit path: every operand is unit-stride or broadcast along the vector dimension, and quad-aligned elsewhere
+    int vec = 4;
+    unsigned vecmask = 0;
+    for (int t = 0; t < S.n_ops && vec == 4; ++t) {
+        const long long vs = row ? P.op_r0s[t] : P.op_os[t][0];
+        if (vs == 0) continue;
+        if (vs != 1 || !aligned32(P.op[t])) { vec = 1; break; }
+        vecmask |= 1u << t;
+        if (row) { if (P.op_r1s[t] % 4) vec = 1; }
+        else { if (P.op_r0s[t] % 4 || P.op_r1s[t] % 4) vec = 1; }
+        for (int k = row ? 0 : 1; k < 3; ++k) if (P.op_os[t][k] % 4) vec = 1;
     }
-    const long long groups_per_block = 256 / G;
-    long long blocks_x = (O + groups_per_block - 1) / groups_per_block;
-    const long long target = 148LL * 8;
+    if (row && (R0 % 4)) vec = 1;
+    if (vecmask == 0) vec = 1;
+    P.vecmask = vecmask;
+
+    long long NG, Rl;        // groups that own outputs, flattened summed length in loop units
+    int width;
+    if (row) {
+        NG = O;
+        Rl = vec == 4 ? R / 4 : R;
+        P.r0div = make_fd((unsigned)(vec == 4 ? R0 / 4 : R0));
+        for (int k = 0; k < 3; ++k) P.odiv[k] = make_fd(k < S.n_o ? (unsigned)S.odim[k] : 1u);
+        width = (O < 148LL * 16) ? 256 : 32;          // few outputs: a whole CTA per output
+        P.fin_vec = 1;
+    } else {
+        const long long Q0 = (O0 + vec - 1) / vec;
+        NG = Q0;
+        for (int k = 1; k < S.n_o; ++k) NG *= S.odim[k];
+        Rl = R;
+        P.r0div = make_fd((unsigned)R0);
+        P.odiv[0] = make_fd((unsigned)Q0);
+        for (int k = 1; k < 3; ++k) P.odiv[k] = make_fd(k < S.n_o ? (unsigned)S.odim[k] : 1u);
+        width = (R >= 64) ? 8 : 1;                    // warps of a CTA share the summed range when it is long enough
+        P.fin_vec = vec;
+        bool ov = P.out_s[0] == 1 && aligned32(P.out);
+        for (int k = 1; k < 3; ++k) if (P.out_s[k] % 4) ov = false;
+        P.out_vec = ov ? 1u : 0u;
+    }
+    P.NG = (unsigned)NG;
+    Red3Kernel kernel = nullptr;
+    switch (P.n_ops) {
+        case 1: kernel = red3_kernel<1>(row, width, vec); break;
+        case 2: kernel = red3_kernel<2>(row, width, vec); break;
+        case 3: kernel = red3_kernel<3>(row, width, vec); break;
+        default: kernel = red3_kernel<4>(row, width, vec); break;
+    }
+    const long long groups_per_cta = 256 / width;
+    const long long blocks_x = (NG + groups_per_cta - 1) / groups_per_cta;
+    // Slicing the summed range: below eight waves of CTAs, slice until the tail is < 1/8 of the run (one-shot grids
+    // of many short CTAs stream best on B200, tools/probe_stream.cu).  Every slice keeps >= 2 trips.
+    const long long per_trip = (long long)width * RED_U;
+    const long long slots = red3_slots(kernel);
+    const long long max_splits = Rl / (per_trip * 2) > 0 ? Rl / (per_trip * 2) : 1;
     long long splits = 1;
-    const long long per_iter = (long long)G * VEC * 4;          // summed elements one group covers per loop trip
-    if (blocks_x < target) {
-        splits = (target + blocks_x - 1) / blocks_x;
-        const long long max_splits = R / (per_iter * 2) > 0 ? R / (per_iter * 2) : 1;
-        if (splits > max_splits) splits = max_splits;
-        if (splits > 2048) splits = 2048;
+    if (blocks_x < 8 * slots) splits = (8 * slots + blocks_x - 1) / blocks_x;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    long long chunk = (Rl + splits - 1) / splits;
+    chunk = (chunk + per_trip - 1) / per_trip * per_trip;
+    splits = (Rl + chunk - 1) / chunk;
+    if (splits > 1) {
+        P.counter = red3_counters(blocks_x);
+        if (!P.counter) { splits = 1; chunk = Rl; }
     }
-    if (blocks_x > target * 8) blocks_x = target * 8;
-    long long chunk = (R + splits - 1) / splits;
-    chunk = (chunk + per_iter - 1) / per_iter * per_iter;        // keeps 128-bit loads aligned across splits
-    splits = (R + chunk - 1) / chunk;
+    P.R = (unsigned)Rl;
     P.chunk = (unsigned)chunk;
     P.splits = (int)splits;
     if (splits > 1) {
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&P.partial), (size_t)splits * O * sizeof(double), st);
-        if (e != cudaSuccess) return set_error("reduce: workspace allocation failed: %s", cudaGetErrorString(e));
+        P.partial = red3_workspace(st, (size_t)splits * NG * P.fin_vec * sizeof(double));
+        if (!P.partial) return set_error("reduce: workspace allocation failed");
     }
     dim3 grid((unsigned)blocks_x, (unsigned)splits, 1);
-    if (G == 256) { if (VEC == 2) launch_reduce2<256, 2>(P, grid, st); else launch_reduce2<256, 1>(P, grid, st); }
-    else if (G == 32) { if (VEC == 2) launch_reduce2<32, 2>(P, grid, st); else launch_reduce2<32, 1>(P, grid, st); }
-    else launch_reduce2<1, 1>(P, grid, st);
+    kernel<<<grid, 256, 0, st>>>(P);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error("reduce2 launch failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return set_error("reduce launch failed: %s", cudaGetErrorString(e));
     count_launch();
-    if (splits > 1) {
-        long long fb = (O + 255) / 256;
-        if (fb > 148 * 8) fb = 148 * 8;
-        reduce2_finalize_kernel<<<(unsigned)fb, 256, 0, st>>>(P);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return set_error("reduce2 finalize launch failed: %s", cudaGetErrorString(e));
-        count_launch();
-        cudaFreeAsync(P.partial, st);
-    }
     return 0;
 }
 
@@ -392,7 +619,7 @@ static void launch_reduce(const RedParams& P, dim3 grid, cudaStream_t st) {
 int reduce_run(const ReduceSpec& S, cudaStream_t st) {
     if (S.n_ops < 1 || S.n_ops > ADB_RED_MAX_OPS) return set_error("reduce: %d operands (max %d)", S.n_ops, ADB_RED_MAX_OPS);
     {
-        const int rc = reduce2_try(S, st);
+        const int rc = reduce3_try(S, st);
         if (rc >= 0) return rc;
     }
     RedParams P;
