@@ -13,3 +13,4 @@ from .core.wrappers import checkpoint
 from .core.conv import Col2Im, Conv2D, Im2Col
 from .core.grad import grad
 from .device import DeviceArray, ewise_stats, force_interpreter, init, launch_count, pinned_empty, precision, set_precision, synchronize, to_device, to_host, use_stream
+from .core.engine import eval_many, evaluate_many

@@ -8,7 +8,7 @@ import numpy as np
 
 from .. import _lib
 from ..device import DeviceArray, stream_ptr, to_device, torch
-from .node import Node, Variable
+from .node import ConstFill, Node, Variable
 
 fusion_enabled = True   # set False to run one kernel per node (debugging / A-B measurements)
 kernel_timings = None   # bench.py sets this to a list; Einsum then records (description, start, stop) CUDA events
@@ -155,6 +155,97 @@ def evaluate_many(tops, on_ready=None):
 
 def evaluate(top):
     evaluate_many([top])
+
+
+# ------------------------------------------------------------------------------------------- pipelined host API
+_side_streams = None
+PIPELINE_MIN_BYTES = 1 << 20      # results smaller than this are read back by the plain synchronous path at the end
+
+
+def _streams():
+    global _side_streams
+    if _side_streams is None:
+        t = torch()
+        _side_streams = (t.cuda.Stream(), t.cuda.Stream())
+    return _side_streams
+
+
+def _host_leaves(top, seen):
+    """Leaves under `top` (within the not-yet-evaluated sub-DAG) whose host ndarray still has to be uploaded."""
+    out, stack = [], [top]
+    while stack:
+        n = stack.pop()
+        if id(n) in seen:
+            continue
+        seen.add(id(n))
+        if isinstance(n, Variable):
+            if isinstance(n, ConstFill) and n.fill is not None and n._host is None:
+                continue                       # never materialised: a one-element broadcast on the device
+            if n._dev is None and scalar_of(n) is None:
+                v = n._host if n._host is not None else n._value
+                if isinstance(v, np.ndarray) and v.size > 0:
+                    out.append((n, v))         # small leaves too: a synchronous upload would wait for every queued kernel
+            continue
+        if _has_value(n) or not _is_device_node(n):
+            continue
+        stack.extend(n.children)
+    return out
+
+
+def eval_many(tops):
+    """`[t() for t in tops]` as ONE pipelined pass: returns the host values (and memoises them in `node.cached`, as
+    reference node.py:42-46 does), but the host->device copies of the leaves, the kernels, and the device->host
+    copies of the results run on three streams - uploads of later outputs' operands and downloads of earlier
+    outputs overlap the kernels in between.  Values are identical to evaluating the nodes one by one."""
+    tops = list(tops)
+    t = torch()
+    from ..device import enqueue_download, to_device_async
+    h2d, d2h = _streams()
+    compute = t.cuda.current_stream()
+    pending = [x for x in tops if x._host is None]
+    todo = [x for x in pending if x._dev is None]
+    # 1. queue every large leaf upload, in the order the outputs need them
+    seen, per_top, keep = set(), {}, []
+    start = t.cuda.Event()
+    start.record(compute)             # recycled allocator blocks may still be in use by kernels queued earlier
+    h2d.wait_event(start)
+    for x in todo:
+        evs = []
+        for leaf, value in _host_leaves(x, seen):
+            leaf._dev, staged = to_device_async(value, h2d)
+            keep.append(staged)
+            ev = t.cuda.Event()
+            ev.record(h2d)
+            evs.append(ev)
+        per_top[id(x)] = evs
+    # 2. kernels per output; each result's download is queued behind its own kernels only
+    plan = _plan(todo)
+    results = {}
+    for x in pending:
+        for ev in per_top.get(id(x), ()):
+            compute.wait_event(ev)
+        if x._dev is None:
+            _execute(x, plan)
+        if x._dev is None:            # foreign (numpy) node: already has its host value
+            continue
+        d = x._dev
+        if d.size * 8 >= PIPELINE_MIN_BYTES:
+            done = t.cuda.Event()
+            done.record(compute)
+            d2h.wait_event(done)
+            host = enqueue_download(d, d2h)
+            if host is not None:
+                results[id(x)] = host
+    d2h.synchronize()
+    compute.synchronize()
+    check_pending_flags()
+    del keep
+    out = []
+    for x in tops:
+        if x._host is None and id(x) in results:
+            x._host = results[id(x)]
+        out.append(x.eval())
+    return out
 
 
 def dev(node):

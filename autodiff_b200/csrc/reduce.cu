@@ -738,16 +738,118 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const double* __restric
     }
 }
 
+// Wide rows: one CTA per row, the row of logits AND labels held in registers (K quads per thread each), so HBM is
+// read exactly once; three block reductions (max, [sum exp, sum labels], dot).  cols <= 256 * 4 * K.
+__device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();                       // previous use of sm is over
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    return t;
+}
+__device__ __forceinline__ double block_reduce_max(double v, double* sm) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = sm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = fmax(t, sm[w]);
+    return t;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) softmax_ce_wide_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
+                                                              long long z_sr, double* __restrict__ out, long long o_s, long long rows,
+                                                              unsigned cols, int* __restrict__ flag) {
+    __shared__ double sm[8];
+    __shared__ int sm_nan;
+    const long long r = blockIdx.x;
+    const double* z = logits + r * z_sr;
+    const double* l = labels + r * l_sr;
+    Quad zq[K], lq[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const unsigned c = (k * 256u + threadIdx.x) * 4u;
+        if (c + 3 < cols) {
+            zq[k] = ldq(z + c);
+            lq[k] = ldq(l + c);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                zq[k].v[e] = c + e < cols ? __ldg(z + c + e) : -INFINITY;   // exp(-inf - mx) = 0, label 0: no contribution
+                lq[k].v[e] = c + e < cols ? __ldg(l + c + e) : 0.0;
+            }
+        }
+    }
+    if (threadIdx.x == 0) sm_nan = 0;
+    double mx = -INFINITY;
+    bool nan_seen = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { nan_seen |= (zq[k].v[e] != zq[k].v[e]); mx = fmax(mx, zq[k].v[e]); }
+    }
+    mx = block_reduce_max(mx, sm);
+    if (nan_seen) sm_nan = 1;
+    __syncthreads();
+    if (sm_nan) mx = NAN;      // np.max propagates NaN
+    double se = 0.0, lsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned c = (k * 256u + threadIdx.x) * 4u + e;
+            if (c < cols) se += exp(zq[k].v[e] - mx);
+            lsum += lq[k].v[e];
+        }
+    }
+    se = block_reduce_sum(se, sm);
+    lsum = block_reduce_sum(lsum, sm);
+    const double lse = mx + log(se);
+    double sdot = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned c = (k * 256u + threadIdx.x) * 4u + e;
+            if (c < cols) sdot += lq[k].v[e] * zq[k].v[e] - lq[k].v[e] * lse;
+        }
+    }
+    sdot = block_reduce_sum(sdot, sm);
+    if (threadIdx.x == 0) {
+        out[r * o_s] = -sdot;
+        if (!(fabs(lsum - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+    }
+}
+
 int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st) {
     if (labels->rank != 2 || logits->rank != 2) return set_error("softmax_ce: labels and logits must be 2-D (got %d, %d)", labels->rank, logits->rank);
     const long long rows = logits->shape[0], cols = logits->shape[1];
     if (labels->shape[0] != rows || labels->shape[1] != cols) return set_error("softmax_ce: labels %lldx%lld vs logits %lldx%lld", (long long)labels->shape[0], (long long)labels->shape[1], rows, cols);
     if (out->rank != 1 || out->shape[0] != rows) return set_error("softmax_ce: out must have %lld elements", rows);
     if (rows == 0) return 0;
-    long long blocks = (rows + 7) / 8;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    softmax_ce_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels->ptr, labels->stride[0], labels->stride[1], logits->ptr, logits->stride[0],
-                                                        logits->stride[1], out->ptr, out->stride[0], rows, cols, flag);
+    const bool quad_ok = labels->stride[1] == 1 && logits->stride[1] == 1 && aligned32(labels->ptr) && aligned32(logits->ptr) &&
+                         labels->stride[0] % 4 == 0 && logits->stride[0] % 4 == 0;
+    if (quad_ok && cols >= 512 && cols <= 4096 && rows < (1LL << 31)) {
+        const unsigned g = (unsigned)rows;
+#define ADB_SCE(KK) softmax_ce_wide_kernel<KK><<<g, 256, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
+                                                                  out->stride[0], rows, (unsigned)cols, flag)
+        if (cols <= 1024) ADB_SCE(1);
+        else if (cols <= 2048) ADB_SCE(2);
+        else ADB_SCE(4);
+#undef ADB_SCE
+    } else {
+        long long blocks = (rows + 7) / 8;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        softmax_ce_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels->ptr, labels->stride[0], labels->stride[1], logits->ptr, logits->stride[0],
+                                                            logits->stride[1], out->ptr, out->stride[0], rows, cols, flag);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("softmax_ce launch failed: %s", cudaGetErrorString(e));
     count_launch();

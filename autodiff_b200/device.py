@@ -236,12 +236,65 @@ class DeviceArray:
 
 
 # --------------------------------------------------------------------------------------- host <-> device
+class _PinnedBlock:
+    """One cudaMallocHost allocation; goes back to the pool when the last numpy view of it dies."""
+    __slots__ = ("ptr", "cap", "__weakref__")
+
+    def __init__(self, ptr, cap):
+        self.ptr, self.cap = ptr, cap
+
+    def __del__(self):
+        try:
+            _pinned_free.setdefault(self.cap, []).append(self.ptr)
+        except Exception:      # interpreter shutdown
+            pass
+
+
+_pinned_free = {}      # capacity -> [host pointers]; page-locked memory is expensive to create (~0.3 s/GiB), so it is recycled
+_PINNED_GRAIN = 1 << 21
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array backed by page-locked memory (torch's caching host allocator)."""
-    t = torch()
+    """numpy array backed by page-locked memory from a size-class pool (cudaMallocHost through the C ABI); the block
+    returns to the pool when the array and all its views are garbage collected."""
     n = int(np.prod(shape, dtype=np.int64))
-    buf = t.empty(max(n, 1), dtype=getattr(t, np.dtype(dtype).name), pin_memory=t.cuda.is_available())
-    return buf.numpy()[:n].reshape(shape)
+    nbytes = max(n, 1) * np.dtype(dtype).itemsize
+    if not torch().cuda.is_available():
+        return np.empty(shape, dtype=dtype)
+    cap = (nbytes + _PINNED_GRAIN - 1) // _PINNED_GRAIN * _PINNED_GRAIN
+    free = _pinned_free.get(cap)
+    if free:
+        ptr = free.pop()
+    else:
+        out = C.c_void_p()
+        _lib.check(_lib.lib().adb_host_alloc(C.byref(out), cap))
+        ptr = out.value
+    block = _PinnedBlock(ptr, cap)
+    raw = (C.c_char * nbytes).from_address(ptr)
+    raw._adb_block = block                      # numpy keeps `raw` alive as the array's base
+    return np.frombuffer(raw, dtype=dtype, count=n).reshape(shape)
+
+
+def _enqueue_upload(a, out, st):
+    """Queues the host->device copy of fp64 ndarray `a` into DeviceArray `out` on stream `st` (a c_void_p)."""
+    L = _lib.lib()
+    if a.ndim >= 2 and a.strides[-1] == 8 and _rows_regular(a):
+        rows = a.size // a.shape[-1]
+        src_pitch = a.strides[-2] if a.shape[-2] > 1 else a.shape[-1] * 8
+        if all(d == 1 for d in a.shape[:-1]):
+            src_pitch = a.shape[-1] * 8
+        _lib.check(L.adb_memcpy2d_h2d(C.c_void_p(out.ptr), out.strides[-2] * 8 if out.ndim >= 2 else a.shape[-1] * 8,
+                                      C.c_void_p(a.ctypes.data), src_pitch, a.shape[-1] * 8, rows, st))
+        return a
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    if a.ndim >= 2:
+        rows = a.size // a.shape[-1]
+        _lib.check(L.adb_memcpy2d_h2d(C.c_void_p(out.ptr), out.strides[-2] * 8, C.c_void_p(a.ctypes.data), a.shape[-1] * 8,
+                                      a.shape[-1] * 8, rows, st))
+    else:
+        _lib.check(L.adb_memcpy_h2d(C.c_void_p(out.ptr), C.c_void_p(a.ctypes.data), a.size * 8, st))
+    return a
 
 
 def to_device(array):
@@ -256,26 +309,42 @@ def to_device(array):
     out = DeviceArray.empty(a.shape)
     if a.size == 0:
         return out
-    L = _lib.lib()
-    st = C.c_void_p(stream_ptr())
-    if a.ndim >= 2 and a.strides[-1] == 8 and _rows_regular(a):
-        rows = a.size // a.shape[-1]
-        src_pitch = a.strides[-2] if a.shape[-2] > 1 else a.shape[-1] * 8
-        if all(d == 1 for d in a.shape[:-1]):
-            src_pitch = a.shape[-1] * 8
-        _lib.check(L.adb_memcpy2d_h2d(C.c_void_p(out.ptr), out.strides[-2] * 8 if out.ndim >= 2 else a.shape[-1] * 8,
-                                      C.c_void_p(a.ctypes.data), src_pitch, a.shape[-1] * 8, rows, st))
-    else:
-        if not a.flags.c_contiguous:
-            a = np.ascontiguousarray(a)
-        if a.ndim >= 2:
-            rows = a.size // a.shape[-1]
-            _lib.check(L.adb_memcpy2d_h2d(C.c_void_p(out.ptr), out.strides[-2] * 8, C.c_void_p(a.ctypes.data), a.shape[-1] * 8,
-                                          a.shape[-1] * 8, rows, st))
-        else:
-            _lib.check(L.adb_memcpy_h2d(C.c_void_p(out.ptr), C.c_void_p(a.ctypes.data), a.size * 8, st))
+    _enqueue_upload(a, out, C.c_void_p(stream_ptr()))
     synchronize()   # the source may be pageable and may be mutated/freed by the caller right after
     return out
+
+
+def to_device_async(array, stream):
+    """Like to_device, but the copy is only QUEUED on `stream` (a torch.cuda.Stream).  Returns (DeviceArray, keepalive):
+    the caller orders consumers after the copy with an event and keeps `keepalive` (the staged source) alive until then."""
+    _ensure_init()
+    a = np.asarray(array)
+    if a.dtype != np.float64:
+        a = a.astype(np.float64)
+    out = DeviceArray.empty(a.shape)
+    if a.size == 0:
+        return out, a
+    keep = _enqueue_upload(a, out, C.c_void_p(stream.cuda_stream))
+    return out, keep
+
+
+def enqueue_download(d, stream):
+    """Queues the device->host copy of DeviceArray `d` on `stream` into a fresh pinned buffer; returns the ndarray
+    (valid once the stream has been synchronised), or None when `d` needs a gather first (the caller falls back)."""
+    L = _lib.lib()
+    st = C.c_void_p(stream.cuda_stream)
+    if d.size == 0:
+        return np.empty(d.shape, dtype=np.float64)
+    out = pinned_empty(d.shape) if d.size >= 4096 else np.empty(d.shape, dtype=np.float64)
+    if d.is_dense():
+        _lib.check(L.adb_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(d.ptr), d.size * 8, st))
+        return out
+    if d.ndim >= 2 and d.strides[-1] == 1 and _dev_rows_regular(d):
+        rows = d.size // d.shape[-1]
+        _lib.check(L.adb_memcpy2d_d2h(C.c_void_p(out.ctypes.data), d.shape[-1] * 8, C.c_void_p(d.ptr), d.strides[-2] * 8,
+                                      d.shape[-1] * 8, rows, st))
+        return out
+    return None
 
 
 def _rows_regular(a):

@@ -401,3 +401,90 @@ def test_catalogued_programs_match_interpreter_bitwise():
             assert np.array_equal(w, g), "graph %d shape %s: static and interpreted programs differ" % (i, shp)
     stats = ad.ewise_stats()
     assert " static " in stats and " interp " in stats
+
+
+# ------------------------------------------------------------------------------------- streaming reductions / wide CE
+@pytest.mark.parametrize("cols", [512, 515, 1000, 1024, 2049, 4096, 4100, 5000])
+def test_softmax_ce_wide_rows(cols, ad):
+    """One-CTA-per-row register-resident kernel (512 <= cols <= 4096, ragged tails) and the multi-pass fallback."""
+    rng = np.random.default_rng(cols)
+    z = rng.standard_normal((67, cols)) * 4
+    lab = rng.random((67, cols)); lab /= lab.sum(1, keepdims=True)
+    got = ad.SoftmaxCEWithLogits(labels=ad.Variable(lab, name="l"), logits=ad.Variable(z, name="z"))()
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    assert got.shape == ref.shape
+    check(got, ref)
+    z[5, 7] = np.nan
+    got = ad.SoftmaxCEWithLogits(labels=ad.Variable(lab, name="l"), logits=ad.Variable(z, name="z"))()
+    assert np.isnan(got[5]) and not np.isnan(got[4])
+    bad = lab.copy(); bad[66] *= 1.01
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        ad.SoftmaxCEWithLogits(labels=ad.Variable(bad, name="l"), logits=ad.Variable(z, name="z"))()
+
+
+REDUCTIONS = [
+    ("ab->a", [(300, 4096)]), ("ab->a", [(77, 1031)]), ("ab->b", [(4096, 300)]), ("ab->b", [(1031, 77)]), ("ab->b", [(9, 5000)]),
+    ("ab->", [(2048, 2048)]), ("ab->", [(1, 7)]), ("a->", [(1000003,)]), ("abc->b", [(61, 130, 67)]), ("abc->ac", [(61, 130, 68)]),
+    ("abc->c", [(61, 130, 68)]), ("abc->a", [(61, 130, 68)]), ("abcd->bd", [(12, 20, 14, 36)]), ("abcd->ac", [(12, 20, 14, 36)]),
+    ("ijkl,jl->ik", [(24, 20, 28, 32), (20, 32)]), ("ijkl,ik->jl", [(24, 20, 28, 32), (24, 28)]),
+    ("ijkl,jl->ik", [(9, 11, 13, 15), (11, 15)]), ("ijkl,ik->jl", [(9, 11, 13, 15), (9, 13)]),
+    ("bi,o->bo", [(257, 1000), (1,)]), ("ab,ab->a", [(130, 2048), (130, 2048)]), ("ab,ab->b", [(2048, 132), (2048, 132)]),
+    ("ab,b->a", [(300, 1024), (1024,)]), ("ab,a->b", [(1024, 300), (1024,)]), ("ab,bc,c->a", [(40, 300), (300, 9), (9,)]),
+]
+
+
+@pytest.mark.parametrize("spec,shapes", REDUCTIONS)
+def test_streaming_reductions_vs_numpy(spec, shapes, ad):
+    """Row / column streaming kernels incl. sliced summed ranges (few outputs), ragged quads and the scalar fallbacks."""
+    rng = np.random.default_rng(abs(hash(spec)) % 1000 + len(shapes[0]))
+    ops = [rng.standard_normal(s) for s in shapes]
+    got = ad.Einsum(spec, *[ad.Variable(o, name="o%d" % i) for i, o in enumerate(ops)])()
+    ref = np.einsum(spec, *ops)
+    assert np.shape(got) == ref.shape
+    # cancellation: hold the error to 1e-12 of the sum of magnitudes (what a reordered fp64 sum can guarantee)
+    scale = np.einsum(spec, *[np.abs(o) for o in ops]).max()
+    assert np.max(np.abs(np.asarray(got) - ref)) <= 1e-12 * scale
+    # a strided (sliced) view of the first operand takes the unaligned / scalar path
+    if ops[0].ndim >= 2 and ops[0].shape[-1] > 4:
+        view = ops[0][..., 1:-1]
+        rest = [o[..., 1:-1] if (sub[-1] == spec.split("->")[0].split(",")[0][-1]) else o
+                for sub, o in zip(spec.split("->")[0].split(",")[1:], ops[1:])]
+        try:
+            ref2 = np.einsum(spec, view, *rest)
+        except ValueError:
+            return
+        got2 = ad.Einsum(spec, ad.Variable(view, name="v"), *[ad.Variable(o, name="r%d" % i) for i, o in enumerate(rest)])()
+        scale2 = np.einsum(spec, np.abs(view), *[np.abs(o) for o in rest]).max()
+        assert np.max(np.abs(np.asarray(got2) - ref2)) <= 1e-12 * scale2
+
+
+def test_frobenius_norm_large(ad):
+    rng = np.random.default_rng(3)
+    xs = [rng.standard_normal((1031, 517)), rng.standard_normal((4097, 64)), rng.standard_normal(11)]
+    got = ad.FrobeniusNorm(*[ad.Variable(x, name="x%d" % i) for i, x in enumerate(xs)])()
+    check(got, np.sqrt(sum(np.sum(np.square(x)) for x in xs)))
+
+
+def test_eval_many_pipelined_matches_sequential(ad):
+    """ad.eval_many == [n() for n in nodes] (bitwise), incl. large leaves (async upload path), pitched / strided
+    results, small results, shared leaves and already-evaluated nodes."""
+    rng = np.random.default_rng(11)
+    a, b = rng.standard_normal((700, 515)), rng.standard_normal((515, 600))
+    c = rng.standard_normal((700, 600))
+
+    def graphs():
+        A, B, Cc = ad.Variable(a, name="a"), ad.Variable(b, name="b"), ad.Variable(c, name="c")
+        e = A @ B
+        da, db = ad.grad(e, [A, B])
+        return [e, da, db, ad.ReLU(e + Cc), ad.Einsum("ab->", e), ad.Transpose(Cc), A]
+    want = [np.asarray(n()) for n in graphs()]
+    nodes = graphs()
+    got = ad.eval_many(nodes)
+    assert len(got) == len(want)
+    for g, w, n in zip(got, want, nodes):
+        assert np.shape(g) == np.shape(w)
+        assert np.array_equal(np.asarray(g), w)
+        assert n.cached is g or np.array_equal(np.asarray(n.cached), w)
+    again = ad.eval_many(nodes)            # memoised
+    for g, w in zip(again, want):
+        assert np.array_equal(np.asarray(g), w)
