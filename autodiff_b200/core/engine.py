@@ -15,11 +15,17 @@ kernel_timings = None   # bench.py sets this to a list; Einsum then records (des
 _pending_flags = []   # (torch int32 tensor, exception) raised at the next host synchronisation
 
 
+_device_class = {}
+
+
 def _is_device_node(node):
     if "_eval" in node.__dict__:
         return False
-    cls_eval = type(node)._eval
-    return cls_eval is Node._eval or isinstance(node, Variable)
+    cls = type(node)
+    r = _device_class.get(cls)
+    if r is None:
+        r = _device_class[cls] = cls._eval is Node._eval or issubclass(cls, Variable)
+    return r
 
 
 def _has_value(node):

@@ -206,11 +206,12 @@ class Variable(Node):
             return None
         else:
             v = self._value
-        if isinstance(v, DeviceArray):
+        tv = type(v)
+        if tv is np.ndarray:
+            return float(v) if v.ndim == 0 else None
+        if tv is DeviceArray:
             return None
-        if isinstance(v, numbers.Number):
-            return float(v)
-        if isinstance(v, np.ndarray) and v.ndim == 0:
+        if tv is float or tv is int or isinstance(v, numbers.Number):
             return float(v)
         return None
 
@@ -293,10 +294,16 @@ class ConstFill(Variable):
         return Variable._eval_device(self)
 
 
-@contextmanager
-def add_context(ctx):
-    Node.context_list.append(ctx + "_" + str(time.time()))
-    try:
-        yield
-    finally:
+class add_context:
+    """Name scope (reference node.py:140-146): pushes `ctx_<timestamp>` on Node.context_list for the `with` body."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def __enter__(self):
+        Node.context_list.append(self.ctx + "_" + str(time.time()))
+
+    def __exit__(self, *exc):
         del Node.context_list[-1]
+        return False

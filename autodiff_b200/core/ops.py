@@ -20,6 +20,7 @@ from .. import _lib
 from ..device import DeviceArray, stream_ptr, torch
 from . import engine
 from .engine import dev, run_program, scalar_of
+from .fusion import broadcast_shapes
 from .node import ConstFill, Node, Variable, add_context
 from .reshape import ReduceSumKeepDims
 
@@ -43,7 +44,7 @@ def shape_from_elems(*elems):
     """Broadcast shape of the children (reference ops.py:23-26, which allocates np.ones per child to find it)."""
     if len(elems) == 0:
         return 1,
-    return np.broadcast_shapes(*[tuple(elem.shape) for elem in elems])
+    return broadcast_shapes(*[elem.shape for elem in elems])
 
 
 @module_wrapper
