@@ -35,10 +35,12 @@ constexpr int BK = 16;
 // Tile configuration: 8 warps as 2 (M) x 4 (N); warp tile = (BM/2) x (BN/4) = MT x NT fragments of 8x8.
 //   Big   128x128, 6 stages, 1 CTA/SM  : large contractions (C2a/C2b/C3)
 //   Small  64x64,  6 stages, 2 CTAs/SM : problems with fewer than one wave of 128x128 tiles (char-rnn steps)
-template <int BM_, int BN_, int STAGES_, int MINB_>
+template <int BM_, int BN_, int STAGES_, int MINB_, int WM_ = 2, int WN_ = 4>
 struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_;
-    static constexpr int MT = BM_ / 16, NT = BN_ / 32;        // fragments per warp
+    static constexpr int WM = WM_, WN = WN_;                  // warp grid (WM x WN = 8 consumer warps)
+    static constexpr int MT = BM_ / (8 * WM_), NT = BN_ / (8 * WN_);   // 8-wide MMA fragments per warp
+    static_assert(WM_ * WN_ == 8 && MT % 2 == 0 && NT % 2 == 0, "warp grid must use 8 warps and even fragment counts");
     static constexpr int A_TILE_BYTES = BM_ * BK * 8;
     static constexpr int B_TILE_BYTES = BN_ * BK * 8;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
@@ -47,6 +49,9 @@ struct TileCfg {
 };
 using CfgBig = TileCfg<128, 128, 6, 1>;
 using CfgSmall = TileCfg<64, 64, 6, 2>;
+// Tall-and-skinny problems (im2col convolutions: M = batch*OH*OW, N = output channels <= 32): all 8 warps stack along M
+// and share the whole 32-column B tile, so no MMA work is spent on padding columns.
+using CfgSkinny = TileCfg<256, 32, 6, 1, 8, 1>;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = CONSUMER_WARPS * 32;   // 9 warps would round to 12 for register allocation (168 regs)
 
@@ -170,9 +175,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kt = 0; kt < npre; ++kt) issue_tile(kt);
     }
 
-    // ===== consumers: 2 (M) x 4 (N) warps, warp tile (BM/2) x (BN/4) =====
-    const int warp_m = warp & 1;
-    const int warp_n = warp >> 1;
+    // ===== consumers: WM (M) x WN (N) warps, warp tile (BM/WM) x (BN/WN) =====
+    constexpr int WM = Cfg::WM, WN = Cfg::WN;
+    const int warp_m = warp % WM;
+    const int warp_n = warp / WM;
     const int g = lane >> 2;
     const int q = lane & 3;
     const int rmap = (g >> 1) | ((g & 1) << 2);
@@ -184,8 +190,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // per-thread byte offsets inside a stage
-    const int a_off = A_KC ? (warp_m * (BM / 2) + rmap) * 128 : warp_m * (MT / 2) * 2048;
-    const int b_off = A_TILE_BYTES + (B_KC ? (warp_n * (BN / 4) + rmap) * 128 : warp_n * (NT / 2) * 2048);
+    const int a_off = A_KC ? (warp_m * (BM / WM) + rmap) * 128 : warp_m * (MT / 2) * 2048;
+    const int b_off = A_TILE_BYTES + (B_KC ? (warp_n * (BN / WN) + rmap) * 128 : warp_n * (NT / 2) * 2048);
 
     for (int kt = 0; kt < num_kt; ++kt) {
         if (is_producer && kt + PREFETCH < num_kt) issue_tile(kt + PREFETCH);
@@ -256,7 +262,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     double* __restrict__ Cb = p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-        const int row = m0 + warp_m * (BM / 2) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
+        const int row = m0 + warp_m * (BM / WM) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
         if (row >= p.M) continue;
         double* crow = Cb + (long long)row * p.c_sm;
         if (B_KC) {
@@ -264,7 +270,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int col = n0 + warp_n * (BN / 4) + nt * 8 + q + 4 * e;
+                    const int col = n0 + warp_n * (BN / WN) + nt * 8 + q + 4 * e;
                     if (col < p.N) crow[(long long)col * p.c_sn] = acc[mt][nt][e];
                 }
             }
@@ -272,7 +278,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int blk = 0; blk < NT / 2; ++blk) {
                 // thread owns 4 consecutive columns: 4q + {0,1,2,3} = (e=0,j=0),(e=0,j=1),(e=1,j=0),(e=1,j=1)
-                const int col = n0 + warp_n * (BN / 4) + blk * 16 + 4 * q;
+                const int col = n0 + warp_n * (BN / WN) + blk * 16 + 4 * q;
                 const double v0 = acc[mt][2 * blk][0], v1 = acc[mt][2 * blk + 1][0];
                 const double v2 = acc[mt][2 * blk][1], v3 = acc[mt][2 * blk + 1][1];
                 double* cp = crow + (long long)col * p.c_sn;
@@ -412,6 +418,15 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
     if (N == 1 && dd.b_sk == 1) dd.b_sn = (K + 1) & ~1LL;
     if (M == 1 && dd.a_sk != 1) dd.a_sm = 1;
     if (N == 1 && dd.b_sk != 1) dd.b_sn = 1;
+    // Skinny in M (few rows, many columns): compute C^T = B^T A^T so the long extent is tiled along M
+    if (M <= 32 && N >= 256) {
+        adb_gemm_desc t = dd;
+        dd.M = t.N; dd.N = t.M;
+        dd.A = t.B; dd.a_sm = t.b_sn; dd.a_sk = t.b_sk; dd.a_sb = t.b_sb;
+        dd.B = t.A; dd.b_sn = t.a_sm; dd.b_sk = t.a_sk; dd.b_sb = t.a_sb;
+        dd.c_sm = t.c_sn; dd.c_sn = t.c_sm;
+        return gemm_f64(&dd, st, force_path);
+    }
     d = &dd;
     // Operands TMA cannot describe (broadcast / odd pitch / unaligned base / neither stride is 1) are repacked into a
     // dense K-contiguous workspace when the problem is large enough for the DMMA path to pay for the extra pass.
@@ -473,8 +488,9 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             const char* e = getenv("ADB_GEMM_TILE");
             tile_pref = !e ? 0 : (!strcmp(e, "small") ? 1 : (!strcmp(e, "big") ? 2 : 0));
         }
-        const bool small = force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && waste_big > 1.05)));
-        const int bm = small ? CfgSmall::BM : CfgBig::BM, bn = small ? CfgSmall::BN : CfgBig::BN;
+        const bool skinny = force_path == 5 || (force_path == 0 && tile_pref == 0 && N <= 32 && M >= 256);
+        const bool small = !skinny && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && waste_big > 1.05))));
+        const int bm = skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM, bn = skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
         const long long slots = small ? 296 : 148;
         const int total_kt = (int)((K + BK - 1) / BK);
@@ -508,7 +524,12 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
             int rc;
-            if (small) {
+            if (skinny) {
+                if (a_kc && b_kc) rc = launch_tma<CfgSkinny, true, true>(ta, tb, p, (int)batch, splits, st);
+                else if (a_kc && !b_kc) rc = launch_tma<CfgSkinny, true, false>(ta, tb, p, (int)batch, splits, st);
+                else if (!a_kc && b_kc) rc = launch_tma<CfgSkinny, false, true>(ta, tb, p, (int)batch, splits, st);
+                else rc = launch_tma<CfgSkinny, false, false>(ta, tb, p, (int)batch, splits, st);
+            } else if (small) {
                 if (a_kc && b_kc) rc = launch_tma<CfgSmall, true, true>(ta, tb, p, (int)batch, splits, st);
                 else if (a_kc && !b_kc) rc = launch_tma<CfgSmall, true, false>(ta, tb, p, (int)batch, splits, st);
                 else if (!a_kc && b_kc) rc = launch_tma<CfgSmall, false, true>(ta, tb, p, (int)batch, splits, st);
