@@ -200,7 +200,10 @@ static bool try_gemm(const Problem& P, adb_gemm_desc& d) {
     Group gk = collapse_group(K_, true, true, false, 0, 1);
     Group gb = collapse_group(B_, true, true, true, 0, 1);
     if (!gm.ok || !gn.ok || !gk.ok || !gb.ok) return false;
-    if (gm.extent < 16 || gn.extent < 16 || gk.extent < 4) return false;
+    // GEMM needs a tile's worth of rows and columns - except tall-skinny problems (dense layers onto a few classes,
+    // im2col convolutions onto a few channels), which the 256x32 tile configuration of gemm_f64.cu handles well
+    const long long mn_min = gm.extent < gn.extent ? gm.extent : gn.extent, mn_max = gm.extent < gn.extent ? gn.extent : gm.extent;
+    if (gk.extent < 4 || mn_min < 4 || (mn_min < 16 && mn_max < 256)) return false;
     if (gm.sa < 0 || gk.sa < 0 || gk.sb < 0 || gn.sb < 0 || gm.sc < 0 || gn.sc < 0) return false;
     d.batch = gb.extent;
     d.K = gk.extent;
