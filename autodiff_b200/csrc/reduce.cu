@@ -740,6 +740,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const double* __restric
 
 // Wide rows: one CTA per row, the row of logits AND labels held in registers (K quads per thread each), so HBM is
 // read exactly once; three block reductions (max, [sum exp, sum labels], dot).  cols <= 256 * 4 * K.
+template <int NW>
 __device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -748,9 +749,10 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
     __syncthreads();
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[w];
+    for (int w = 0; w < NW; ++w) t += sm[w];
     return t;
 }
+template <int NW>
 __device__ __forceinline__ double block_reduce_max(double v, double* sm) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -759,15 +761,18 @@ __device__ __forceinline__ double block_reduce_max(double v, double* sm) {
     __syncthreads();
     double t = sm[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) t = fmax(t, sm[w]);
+    for (int w = 1; w < NW; ++w) t = fmax(t, sm[w]);
     return t;
 }
 
-template <int K>
-__global__ void __launch_bounds__(256) softmax_ce_wide_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
-                                                              long long z_sr, double* __restrict__ out, long long o_s, long long rows,
-                                                              unsigned cols, int* __restrict__ flag) {
-    __shared__ double sm[8];
+// K quads per thread, NT threads per CTA: cols <= NT * 4 * K.  Wide rows use 512 threads so that 32 warps per SM
+// stay resident (the exp() chain is FP64-pipe work that has to overlap the next row's loads).
+template <int K, int NT>
+__global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
+                                                             long long z_sr, double* __restrict__ out, long long o_s, long long rows,
+                                                             unsigned cols, int* __restrict__ flag) {
+    constexpr int NW = NT / 32;
+    __shared__ double sm[NW];
     __shared__ int sm_nan;
     const long long r = blockIdx.x;
     const double* z = logits + r * z_sr;
@@ -775,7 +780,7 @@ __global__ void __launch_bounds__(256) softmax_ce_wide_kernel(const double* __re
     Quad zq[K], lq[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const unsigned c = (k * 256u + threadIdx.x) * 4u;
+        const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u;
         if (c + 3 < cols) {
             zq[k] = ldq(z + c);
             lq[k] = ldq(l + c);
@@ -795,7 +800,7 @@ __global__ void __launch_bounds__(256) softmax_ce_wide_kernel(const double* __re
 #pragma unroll
         for (int e = 0; e < 4; ++e) { nan_seen |= (zq[k].v[e] != zq[k].v[e]); mx = fmax(mx, zq[k].v[e]); }
     }
-    mx = block_reduce_max(mx, sm);
+    mx = block_reduce_max<NW>(mx, sm);
     if (nan_seen) sm_nan = 1;
     __syncthreads();
     if (sm_nan) mx = NAN;      // np.max propagates NaN
@@ -804,24 +809,24 @@ __global__ void __launch_bounds__(256) softmax_ce_wide_kernel(const double* __re
     for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned c = (k * 256u + threadIdx.x) * 4u + e;
+            const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
             if (c < cols) se += exp(zq[k].v[e] - mx);
             lsum += lq[k].v[e];
         }
     }
-    se = block_reduce_sum(se, sm);
-    lsum = block_reduce_sum(lsum, sm);
+    se = block_reduce_sum<NW>(se, sm);
+    lsum = block_reduce_sum<NW>(lsum, sm);
     const double lse = mx + log(se);
     double sdot = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned c = (k * 256u + threadIdx.x) * 4u + e;
+            const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
             if (c < cols) sdot += lq[k].v[e] * zq[k].v[e] - lq[k].v[e] * lse;
         }
     }
-    sdot = block_reduce_sum(sdot, sm);
+    sdot = block_reduce_sum<NW>(sdot, sm);
     if (threadIdx.x == 0) {
         out[r * o_s] = -sdot;
         if (!(fabs(lsum - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
@@ -836,13 +841,14 @@ int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb
     if (rows == 0) return 0;
     const bool quad_ok = labels->stride[1] == 1 && logits->stride[1] == 1 && aligned32(labels->ptr) && aligned32(logits->ptr) &&
                          labels->stride[0] % 4 == 0 && logits->stride[0] % 4 == 0;
-    if (quad_ok && cols >= 512 && cols <= 4096 && rows < (1LL << 31)) {
+    if (quad_ok && cols >= 512 && cols <= 8192 && rows < (1LL << 31)) {
         const unsigned g = (unsigned)rows;
-#define ADB_SCE(KK) softmax_ce_wide_kernel<KK><<<g, 256, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
-                                                                  out->stride[0], rows, (unsigned)cols, flag)
-        if (cols <= 1024) ADB_SCE(1);
-        else if (cols <= 2048) ADB_SCE(2);
-        else ADB_SCE(4);
+#define ADB_SCE(KK, NTT) softmax_ce_wide_kernel<KK, NTT><<<g, NTT, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
+                                                                            out->stride[0], rows, (unsigned)cols, flag)
+        if (cols <= 1024) ADB_SCE(1, 256);
+        else if (cols <= 2048) ADB_SCE(2, 256);
+        else if (cols <= 4096) ADB_SCE(2, 512);
+        else ADB_SCE(4, 512);
 #undef ADB_SCE
     } else {
         long long blocks = (rows + 7) / 8;

@@ -404,7 +404,7 @@ def test_catalogued_programs_match_interpreter_bitwise():
 
 
 # ------------------------------------------------------------------------------------- streaming reductions / wide CE
-@pytest.mark.parametrize("cols", [512, 515, 1000, 1024, 2049, 4096, 4100, 5000])
+@pytest.mark.parametrize("cols", [512, 515, 1000, 1024, 2049, 4096, 4100, 5000, 8192, 8200])
 def test_softmax_ce_wide_rows(cols, ad):
     """One-CTA-per-row register-resident kernel (512 <= cols <= 4096, ragged tails) and the multi-pass fallback."""
     rng = np.random.default_rng(cols)
