@@ -151,12 +151,14 @@ def _execute(top, plan):
 def evaluate_many(tops, on_ready=None):
     """Evaluates several graph outputs with one fusion plan (consumer counts span all of them).
     `on_ready(node)` fires as soon as each output's kernels are queued (used to overlap all-reduces)."""
+    from .utils import gc_paused
     tops = list(tops)
-    plan = _plan([t for t in tops if not _has_value(t)])
-    for t in tops:
-        _execute(t, plan)
-        if on_ready is not None:
-            on_ready(t)
+    with gc_paused():
+        plan = _plan([t for t in tops if not _has_value(t)])
+        for t in tops:
+            _execute(t, plan)
+            if on_ready is not None:
+                on_ready(t)
 
 
 def evaluate(top):

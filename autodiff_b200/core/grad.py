@@ -2,7 +2,7 @@ import collections
 
 from .node import ConstFill, Variable
 from .ops import Add  # noqa: F401  (grad accumulates with `+=`, i.e. Add nodes, as the reference does)
-from .utils import reverse_topo_sort
+from .utils import gc_paused, reverse_topo_sort
 
 
 def grad(top_node, wrt_list, previous_grad=None):
@@ -18,14 +18,15 @@ def grad(top_node, wrt_list, previous_grad=None):
     if previous_grad is None:
         previous_grad = ConstFill(tuple(top_node.shape), 1.0, name=add_sum_name(top_node))
 
-    dct = collections.defaultdict(lambda: Variable(0))
-    dct[top_node] += previous_grad
+    with gc_paused():
+        dct = collections.defaultdict(lambda: Variable(0))
+        dct[top_node] += previous_grad
 
-    for node in reverse_topo_sort(top_node):
-        for child in set(node.children):
-            dct[child] += node.partial_derivative(wrt=child, previous_grad=dct[node])
+        for node in reverse_topo_sort(top_node):
+            for child in set(node.children):
+                dct[child] += node.partial_derivative(wrt=child, previous_grad=dct[node])
 
-    return [dct[wrt] for wrt in wrt_list]
+        return [dct[wrt] for wrt in wrt_list]
 
 
 def add_sum_name(node):

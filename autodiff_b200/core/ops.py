@@ -290,12 +290,23 @@ class Pow(Node):
 
 
 # ------------------------------------------------------------------------------------------------ einsum
+_split_dots_cache = {}
+_einsum_parse_cache = {}     # (op_str, operand shapes) -> (opnames, all_letters, letter_to_dim, shape); all read-only afterwards
+
+
 class Einsum(Node):
     def __init__(self, op_str, *operands, name="EinSum"):
         super().__init__(list(operands), name + " " + op_str)
         # ellipsis can't be in the middle of op_letters (reference ops.py:127)
         self.op_str = op_str
         self.operands = self.children
+
+        # parsing depends only on (op_str, operand shapes): training loops rebuild the same einsums every step
+        key = (op_str, tuple(tuple(op.shape) for op in self.operands))
+        hit = _einsum_parse_cache.get(key)
+        if hit is not None:
+            self.opnames, self.all_letters, self.letter_to_dim, self.shape = hit
+            return
 
         self.opnames = re.split(",|->", self.op_str)
         self.all_letters = "".join(set("".join(self.opnames[:-1])))
@@ -331,10 +342,18 @@ class Einsum(Node):
             for l in self.letter_to_dim.get(let, [1]):
                 self.shape.append(l)
         self.shape = tuple(self.shape)
+        if len(_einsum_parse_cache) > 4096:
+            _einsum_parse_cache.clear()
+        _einsum_parse_cache[key] = (self.opnames, self.all_letters, self.letter_to_dim, self.shape)
 
     @staticmethod
     def split_dots(op_str):
-        return re.findall(r"\.{3}|\S", op_str)
+        r = _split_dots_cache.get(op_str)
+        if r is None:
+            if len(_split_dots_cache) > 4096:
+                _split_dots_cache.clear()
+            r = _split_dots_cache[op_str] = tuple(re.findall(r"\.{3}|\S", op_str))
+        return r
 
     def _ew_spec(self):
         """'ab->ab' (inserted by ReduceSumToShape, ops.py:31-39) is a pass-through for fusion."""

@@ -15,3 +15,22 @@ def reverse_topo_sort(top_node):
             order.append(node)
             stack.pop()
     return reversed(order)
+
+
+class gc_paused:
+    """Pauses the cyclic garbage collector for a graph-sized burst of allocations.  Graphs are DAGs held by child
+    references only (no cycles), so reference counting frees them; the generational collector would just re-scan the
+    tens of thousands of live nodes of a second-order graph over and over (measured: ~15 % of graph-build time)."""
+    __slots__ = ("was",)
+
+    def __enter__(self):
+        import gc
+        self.was = gc.isenabled()
+        if self.was:
+            gc.disable()
+
+    def __exit__(self, *exc):
+        if self.was:
+            import gc
+            gc.enable()
+        return False
