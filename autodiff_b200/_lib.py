@@ -90,6 +90,19 @@ def lib():
     return _lib
 
 
+_call_hook = None     # set by core/tape.py while a recording evaluation runs: hook(name, fn, args)
+
+
+def call(name, *args):
+    """One C-ABI compute call (everything that launches kernels goes through here so that tapes can log it)."""
+    fn = getattr(lib(), name)
+    rc = fn(*args)
+    if rc != 0:
+        check(rc)
+    if _call_hook is not None:
+        _call_hook(name, fn, args)
+
+
 def check(rc):
     if rc != 0:
         msg = lib().adb_last_error().decode("utf-8", "replace")

@@ -29,7 +29,7 @@ class Im2Col(Node):
         x = dev(self.node)
         out = DeviceArray.empty(self.shape)
         tx, to = x.tensor(), out.tensor()
-        _lib.check(_lib.lib().adb_im2col(C.byref(tx), self.kh, self.kw, C.byref(to), C.c_void_p(stream_ptr())))
+        _lib.call("adb_im2col", C.byref(tx), self.kh, self.kw, C.byref(to), C.c_void_p(stream_ptr()))
         return out
 
     def _partial_derivative(self, wrt, previous_grad):
@@ -59,7 +59,7 @@ class Col2Im(Node):
             cols = dense
         out = DeviceArray.empty(self.shape)
         tc, to = cols.tensor(), out.tensor()
-        _lib.check(_lib.lib().adb_col2im(C.byref(tc), self.kh, self.kw, C.byref(to), C.c_void_p(stream_ptr())))
+        _lib.call("adb_col2im", C.byref(tc), self.kh, self.kw, C.byref(to), C.c_void_p(stream_ptr()))
         return out
 
     def _partial_derivative(self, wrt, previous_grad):
@@ -76,3 +76,9 @@ def Conv2D(x, w):
     cols = Im2Col(x, kh, kw)
     out = Einsum("pk,ko->po", cols, Reshape(w, (kh * kw * c, o)))
     return Reshape(out, (n, h - kh + 1, wd - kw + 1, o))
+
+
+# ------------------------------------------------------------------------------------------------ launch tapes
+from . import tape as _tape  # noqa: E402
+_tape.register(Im2Col, "kh", "kw")
+_tape.register(Col2Im, "shape", "kh", "kw")

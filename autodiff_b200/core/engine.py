@@ -150,15 +150,49 @@ def _execute(top, plan):
 
 def evaluate_many(tops, on_ready=None):
     """Evaluates several graph outputs with one fusion plan (consumer counts span all of them).
-    `on_ready(node)` fires as soon as each output's kernels are queued (used to overlap all-reduces)."""
+    `on_ready(node)` fires as soon as each output's kernels are queued (used to overlap all-reduces).
+    Structures seen before are replayed from a launch tape (core/tape.py) instead of being planned again."""
+    from . import tape
     from .utils import gc_paused
     tops = list(tops)
     with gc_paused():
-        plan = _plan([t for t in tops if not _has_value(t)])
-        for t in tops:
-            _execute(t, plan)
-            if on_ready is not None:
-                on_ready(t)
+        rec, sig, scanned = None, None, None
+        if tape.ENABLED and kernel_timings is None and tape._recorder is None:
+            scanned = tape.scan(tops, scalar_of, _has_value, _is_device_node)
+            if scanned is not None and any(l is None for l in scanned[1]):      # (a graph of leaves only has nothing to replay)
+                order, leaves, sig = scanned
+                sig = (fusion_enabled, len(tops)) + sig
+                tp, should_record = tape.lookup(sig)
+                if tp is not None and tape.replay(tp, order, leaves, tops, _materialise_leaf, add_pending_flag, on_ready):
+                    return
+                if tp is None and should_record:
+                    rec = tape.Recorder()
+        if rec is not None:
+            from .. import device as _device
+            tape._recorder, _lib._call_hook, _device._alloc_hook = rec, rec.on_call, rec.on_alloc
+        try:
+            plan = _plan([t for t in tops if not _has_value(t)])
+            for t in tops:
+                _execute(t, plan)
+                if rec is not None:
+                    rec.top_ends.append(len(rec.calls))
+                if on_ready is not None:
+                    on_ready(t)
+        finally:
+            if rec is not None:
+                tape._recorder, _lib._call_hook, _device._alloc_hook = None, None, None
+        if rec is not None:
+            tape.store(sig, tape.build_tape(rec, scanned[0], scanned[1], len(tops)))
+
+
+def _materialise_leaf(node):
+    """Device value of a leaf (or of a node that only has a host value) without going through evaluate()."""
+    if node._dev is None:
+        if isinstance(node, Variable):
+            node._dev = node._eval_device()
+        else:
+            node._dev = to_device(np.asarray(node._host))
+    return node._dev
 
 
 def evaluate(top):
@@ -318,7 +352,7 @@ def run_program_into(code, inputs, outs):
     prog = _program(code)
     tin = (_lib.Tensor * max(len(inputs), 1))(*[a.tensor() for a in inputs])
     tout = (_lib.Tensor * len(outs))(*[o.tensor() for o in outs])
-    _lib.check(_lib.lib().adb_ewise(prog, len(prog), len(inputs), tin, len(outs), tout, _STREAM()))
+    _lib.call("adb_ewise", prog, len(prog), len(inputs), tin, len(outs), tout, _STREAM())
 
 
 def _STREAM():

@@ -418,11 +418,11 @@ class Einsum(Node):
             t = torch()
             e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.check(_lib.lib().adb_einsum(spec, n, tin, C.byref(tout), C.c_void_p(stream_ptr())))
+            _lib.call("adb_einsum", spec, n, tin, C.byref(tout), C.c_void_p(stream_ptr()))
             e1.record()
             engine.kernel_timings.append((spec.decode() + " " + "|".join(str(op.name) for op in self.operands), e0, e1))
             return out
-        _lib.check(_lib.lib().adb_einsum(spec, n, tin, C.byref(tout), C.c_void_p(stream_ptr())))
+        _lib.call("adb_einsum", spec, n, tin, C.byref(tout), C.c_void_p(stream_ptr()))
         return out
 
     def _partial_derivative(self, wrt, previous_grad):
@@ -490,8 +490,7 @@ class SoftmaxCEWithLogits(Node):
         t = torch()
         flag = t.zeros(1, dtype=t.int32, device="cuda")
         tl, tz, to = lab.tensor(), z.tensor(), out.tensor()
-        _lib.check(_lib.lib().adb_softmax_ce(C.byref(tl), C.byref(tz), C.byref(to), C.c_void_p(flag.data_ptr()),
-                                             C.c_void_p(stream_ptr())))
+        _lib.call("adb_softmax_ce", C.byref(tl), C.byref(tz), C.byref(to), C.c_void_p(flag.data_ptr()), C.c_void_p(stream_ptr()))
         engine.add_pending_flag(flag, ValueError("Labels must be a valid probability distribution!"))
         return out
 
@@ -539,7 +538,7 @@ class FrobeniusNorm(Node):
             x = dev(n)
             part = DeviceArray.empty(())
             tx = x.tensor()
-            _lib.check(_lib.lib().adb_sum_squares(C.byref(tx), C.c_void_p(part.ptr), C.c_void_p(stream_ptr())))
+            _lib.call("adb_sum_squares", C.byref(tx), C.c_void_p(part.ptr), C.c_void_p(stream_ptr()))
             parts.append(part)
         acc = None
         for i in range(0, len(parts), _lib.EW_MAX_IN - 1):
@@ -599,3 +598,13 @@ def Softmax(x):
         return exp / Einsum("abci,o->abco", exp, np.array([1]))
     else:
         raise ValueError("5D tensors not yet supported")
+
+
+# ------------------------------------------------------------------------------------------------ launch tapes
+# classes whose device evaluation depends only on (class, these attributes, children) - see core/tape.py
+from . import tape as _tape  # noqa: E402
+for _cls in (Add, Mul, Negate, Recipr, ReLU, Log, Identity, Exp, Sigmoid, Pow, SoftmaxCEWithLogits, SigmoidCEWithLogits, FrobeniusNorm):
+    _tape.register(_cls)
+_tape.register(NormalDistribution, "mean", "variance")
+_tape.register(Einsum, "op_str")
+_tape.register(ReduceSumKeepDims, "axes")

@@ -32,7 +32,7 @@ class ReduceSumKeepDims(Node):
             return x                      # axes=() (reference ops.py:40 inserts these) or size-1 axes: nothing to add
         out = DeviceArray.empty([1 if i in axes else d for i, d in enumerate(x.shape)])
         tx, to = x.tensor(), out.tensor()
-        _lib.check(_lib.lib().adb_reduce_sum(C.byref(tx), C.byref(to), C.c_void_p(stream_ptr())))
+        _lib.call("adb_reduce_sum", C.byref(tx), C.byref(to), C.c_void_p(stream_ptr()))
         return out
 
     def _partial_derivative(self, wrt, previous_grad):
@@ -192,3 +192,11 @@ def _as_pairs(pad_width, ndim):
     if pw.shape != (ndim, 2):
         raise ValueError("Unable to create correctly shaped tuple from %s" % (pad_width,))
     return [(int(a), int(b)) for a, b in pw]
+
+
+# ------------------------------------------------------------------------------------------------ launch tapes
+from . import tape as _tape  # noqa: E402
+_tape.register(Concat, "axis")
+_tape.register(Reshape, "shape")
+_tape.register(Slice, "slice_val")
+_tape.register(Pad, "_pairs", "constant_values")

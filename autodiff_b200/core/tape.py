@@ -1,0 +1,348 @@
+"""Structure-keyed launch tapes: replaying a graph that is evaluated again and again.
+
+Training loops written against the reference rebuild an ISOMORPHIC graph every step (examples/feedforward_mnist.py
+builds `nn(inp)`, the loss and `ad.grad` inside the loop), and for the launch-bound configs the per-node Python of
+planning, fusing and marshalling dominates (C1: 25 kernels of a few microseconds each; C5: 44 k nodes, 10 k kernels).
+The tape removes that work for every evaluation after the second one of a given structure:
+
+  scan     one pre-order walk of the not-yet-evaluated sub-DAG produces a structural signature - node classes, their
+           static attributes (einsum subscripts, axes, slices ...), leaf kinds/shapes/strides, folded scalar values and
+           the sharing pattern (back-references) - so equal signatures mean "same kernels, same operand wiring";
+  record   the 2nd evaluation of a signature runs the normal planner/executor while every C-ABI compute call (with its
+           ctypes argument structs) and every device allocation is logged; each device pointer in those arguments is
+           resolved to (buffer, byte offset), where a buffer is a leaf's storage, a persistent constant or a slot of the
+           step's arena;
+  replay   later evaluations upload the leaves, allocate ONE arena, patch the pointers in the recorded argument structs
+           and re-issue the calls (the C++ side re-plans tiles / access modes from the actual pointers, so alignment or
+           workspace differences are handled there), then hand every materialised node a `DeviceArray` view of the arena.
+
+Results are bit-identical to the normal path: the same kernels run on the same operands in the same order.  Graphs with
+user-defined numpy nodes, unknown node classes or unresolvable pointers are simply never taped.  `ADB_TAPE=0` disables it.
+"""
+import bisect
+import ctypes as C
+import os
+
+import numpy as np
+
+from .. import _lib
+from .. import device as _device
+from ..device import DeviceArray, torch
+from .node import ConstFill, Node, Variable
+
+ENABLED = os.environ.get("ADB_TAPE", "1") != "0"
+RECORD_AT = 2            # record on the 2nd sighting of a structure, replay from the 3rd
+MAX_TAPES = 64
+SCE_ERROR = "Labels must be a valid probability distribution!"
+
+_seen = {}               # signature -> sightings so far
+_tapes = {}              # signature -> Tape | False (not tapeable)
+_recorder = None         # active Recorder (set while a recording evaluation runs)
+stats = {"replays": 0, "records": 0, "rejected": 0}
+
+# node classes whose device evaluation is a pure function of (class, these attributes, children): filled by register()
+_ATTRS = {}
+
+
+def register(cls, *attrs):
+    _ATTRS[cls] = attrs
+
+
+def _freeze(v):
+    if isinstance(v, (list, tuple)):
+        return tuple(_freeze(x) for x in v)
+    if isinstance(v, slice):
+        return ("slice", v.start, v.stop, v.step)
+    if isinstance(v, np.ndarray):
+        return ("nd", v.shape, v.tobytes()) if v.size <= 16 else None
+    if isinstance(v, (np.integer, np.floating)):
+        return v.item()
+    return v
+
+
+def scan(tops, scalar_of, has_value, is_device_node):
+    """Pre-order walk of the sub-DAG that an evaluation of `tops` would touch.
+    Returns (order, leaves, signature) or None when the graph cannot be taped."""
+    pos, order, leaves, sig = {}, [], [], []
+    stack = list(reversed(tops))
+    attrs_of = _ATTRS
+    while stack:
+        n = stack.pop()
+        p = pos.get(id(n))
+        if p is not None:
+            sig.append(p)                        # sharing: a back-reference to an already visited node
+            continue
+        pos[id(n)] = len(order)
+        order.append(n)
+        if isinstance(n, Variable) or has_value(n):
+            s = scalar_of(n)
+            if s is not None:
+                sig.append(("s", s))             # folded into programs as an immediate: the VALUE is structure
+                leaves.append(n)                 # (uploaded only if some kernel reads it as a tensor, see build_tape)
+                continue
+            if n._dev is not None:
+                d = n._dev
+                if type(d) is not DeviceArray:
+                    return None
+                sig.append(("d", d.shape, d.strides))
+            elif isinstance(n, ConstFill) and n.fill is not None and n._host is None:
+                sig.append(("c", n.fill, n._fill_shape))
+            else:
+                v = n._host if n._host is not None else getattr(n, "_value", None)
+                if isinstance(v, DeviceArray):
+                    sig.append(("d", v.shape, v.strides))
+                elif isinstance(v, np.ndarray):
+                    sig.append(("h", v.shape))
+                else:
+                    return None
+            leaves.append(n)
+            continue
+        leaves.append(None)
+        cls = type(n)
+        attrs = attrs_of.get(cls)
+        if attrs is None or not is_device_node(n) or "_eval_device" in n.__dict__:
+            return None
+        if attrs:
+            key = []
+            for a in attrs:
+                f = _freeze(getattr(n, a))
+                if f is None and getattr(n, a) is not None:
+                    return None
+                key.append(f)
+            sig.append((cls, len(n.children), tuple(key)))
+        else:
+            sig.append((cls, len(n.children)))
+        stack.extend(reversed(n.children))
+    return order, leaves, tuple(sig)
+
+
+# ------------------------------------------------------------------------------------------------ recording
+class Recorder:
+    def __init__(self):
+        self.allocs = []          # (ptr, nbytes, base tensor): every DeviceArray.empty during the recording (kept alive)
+        self.calls = []           # (name, fn, args)
+        self.top_ends = []        # number of calls logged when each top finished
+
+    def on_alloc(self, base):
+        self.allocs.append((base.data_ptr(), base.numel() * 8, base))
+
+    def on_call(self, name, fn, args):
+        # byref(DeviceArray.tensor()) points at a struct CACHED on a live DeviceArray: the tape must own a private copy,
+        # or patching pointers at replay time would corrupt that array's descriptor
+        own = []
+        for a in args:
+            obj = getattr(a, "_obj", None)
+            if isinstance(obj, _lib.Tensor):
+                cp = _lib.Tensor()
+                C.memmove(C.byref(cp), C.byref(obj), C.sizeof(_lib.Tensor))
+                own.append(C.byref(cp))
+            else:
+                own.append(a)
+        self.calls.append((name, fn, own))
+
+
+class _Call:
+    __slots__ = ("fn", "args", "patches", "void_patches", "flag_arg")
+
+
+class Tape:
+    __slots__ = ("n_nodes", "n_ext", "ext_leaf", "leaf_ext", "abs_keep", "slot_off", "arena_elems", "calls", "top_ends", "values")
+
+
+def _tensor_structs(arg):
+    """The adb_tensor structs reachable from one ctypes argument."""
+    if isinstance(arg, _lib.Tensor):
+        return [arg]
+    obj = getattr(arg, "_obj", None)           # C.byref(x)
+    if isinstance(obj, _lib.Tensor):
+        return [obj]
+    if isinstance(arg, C.Array) and getattr(arg, "_type_", None) is _lib.Tensor:
+        return [arg[i] for i in range(len(arg))]
+    return []
+
+
+def build_tape(rec, order, leaves, n_tops):
+    """Resolves every device pointer of the recording; returns a Tape or None."""
+    # --- buffers: [0, n_ext) leaf storages (deduplicated by base pointer), then arena slots
+    ext_ptr, ext_leaf, leaf_ext, ext_size = {}, [], {}, []
+    for i, leaf in enumerate(leaves):
+        if leaf is None:
+            continue
+        d = leaf._dev
+        if d is None:
+            continue                             # a scalar that only ever appeared as an immediate: never uploaded
+        b = d.base.data_ptr()
+        j = ext_ptr.get(b)
+        if j is None:
+            j = ext_ptr[b] = len(ext_leaf)
+            ext_leaf.append(i)
+            ext_size.append(d.base.numel() * 8)
+        leaf_ext[i] = (j, d.offset)
+    n_ext = len(ext_leaf)
+    ranges = []                                  # (start, end, buffer index)
+    for b, j in ext_ptr.items():
+        ranges.append((b, b + ext_size[j], j))
+    slot_off, total = [], 0
+    seen_alloc = set()
+    for ptr, nbytes, _base in rec.allocs:
+        if ptr in ext_ptr:
+            continue                             # a leaf uploaded during the recording: its storage is the leaf's, not the arena's
+        if ptr in seen_alloc:
+            return None                          # address reuse inside one recording: cannot happen while bases are kept alive
+        seen_alloc.add(ptr)
+        slot_off.append(total)
+        ranges.append((ptr, ptr + nbytes, n_ext + len(slot_off) - 1))
+        total += (nbytes // 8 + 31) // 32 * 32   # 256-byte aligned slots
+    abs_keep = []
+    const_ptrs = {t.data_ptr(): t for t in _device._const_cache.values()}
+    ranges.sort()
+    starts = [r[0] for r in ranges]
+
+    def resolve(ptr):
+        k = bisect.bisect_right(starts, ptr) - 1
+        if k >= 0 and ranges[k][0] <= ptr < ranges[k][1]:
+            return ranges[k][2], ptr - ranges[k][0]
+        for cp, t in const_ptrs.items():
+            if cp <= ptr < cp + 16:
+                abs_keep.append(t)               # persistent broadcast constant: absolute address, kept alive by the tape
+                return -1, ptr
+        return None
+
+    tape = Tape()
+    tape.calls = []
+    for name, fn, args in rec.calls:
+        c = _Call()
+        c.fn, c.args, c.patches, c.void_patches, c.flag_arg = fn, list(args), [], [], -1
+        for ai, a in enumerate(args):
+            for ts in _tensor_structs(a):
+                if not ts.ptr:
+                    continue
+                r = resolve(ts.ptr)
+                if r is None:
+                    return None
+                if r[0] >= 0:
+                    c.patches.append((ts, r[0], r[1]))
+            if isinstance(a, C.c_void_p) and a.value:
+                if name == "adb_softmax_ce" and ai == 3:
+                    c.flag_arg = ai              # a fresh zeroed flag per replay
+                elif ai == len(args) - 1:
+                    pass                         # the stream
+                else:
+                    r = resolve(a.value)
+                    if r is None:
+                        return None
+                    if r[0] >= 0:
+                        c.void_patches.append((ai, r[0], r[1]))
+        tape.calls.append(c)
+    # --- where every materialised node's value lives
+    values = []
+    for i, n in enumerate(order):
+        if leaves[i] is not None:
+            continue
+        d = n._dev
+        if d is None:
+            continue
+        r = resolve(d.base.data_ptr() + 8 * d.offset) if d.size > 0 else None
+        if r is None or r[0] < 0:
+            if d.size > 0 and (r is None):
+                return None
+            if r is not None and r[0] < 0:
+                values.append((i, -1, d, None, None))          # a view of a persistent constant: reuse the array object
+                continue
+            values.append((i, -2, d, None, None))              # empty array
+            continue
+        values.append((i, r[0], r[1] // 8, d.shape, d.strides))
+    tape.n_nodes = len(order)
+    tape.n_ext, tape.ext_leaf, tape.leaf_ext = n_ext, ext_leaf, leaf_ext
+    tape.abs_keep = abs_keep
+    tape.slot_off, tape.arena_elems = slot_off, total
+    tape.top_ends = list(rec.top_ends)
+    tape.values = values
+    return tape
+
+
+# ------------------------------------------------------------------------------------------------ replay
+def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
+    """Re-issues the recorded calls for a new, isomorphic graph.  Returns False (nothing done) when the leaves of the
+    new graph alias differently from the recorded ones."""
+    t = torch()
+    for i in tape.leaf_ext:
+        if leaves[i]._dev is None:
+            dev_of(leaves[i])                     # upload (host leaf) or materialise (constant / device value)
+    bases, base_tensors = [0] * tape.n_ext, [None] * tape.n_ext
+    for j, i in enumerate(tape.ext_leaf):
+        d = leaves[i]._dev
+        bases[j] = d.base.data_ptr()
+        base_tensors[j] = d.base
+    for i, (j, off) in tape.leaf_ext.items():
+        d = leaves[i]._dev
+        if d.base.data_ptr() != bases[j] or d.offset != off:
+            return False                          # e.g. two leaves that were views of one array are now separate arrays
+    arena = t.empty(max(tape.arena_elems, 2), dtype=t.float64, device="cuda")
+    a0 = arena.data_ptr()
+    for off in tape.slot_off:
+        bases.append(a0 + 8 * off)
+    n_ext = tape.n_ext
+    # values first: on_ready callbacks (gradient all-reduce) use node._dev as soon as a top's kernels are queued
+    slot_off = tape.slot_off
+    for i, j, off, shape, strides in tape.values:
+        n = order[i]
+        if j >= n_ext:
+            n._dev = DeviceArray(arena, slot_off[j - n_ext] + off, shape, strides)
+        elif j >= 0:
+            n._dev = DeviceArray(base_tensors[j], off, shape, strides)
+        else:
+            n._dev = off                          # recorded DeviceArray (persistent constant / empty)
+    check = _lib.check
+    ends = tape.top_ends
+    ti = 0
+    while on_ready is not None and ti < len(ends) and ends[ti] == 0:
+        on_ready(tops[ti])
+        ti += 1
+    for k, c in enumerate(tape.calls):
+        for ts, j, off in c.patches:
+            ts.ptr = bases[j] + off
+        args = c.args
+        for ai, j, off in c.void_patches:
+            args[ai] = C.c_void_p(bases[j] + off)
+        if c.flag_arg >= 0:
+            flag = t.zeros(1, dtype=t.int32, device="cuda")
+            args[c.flag_arg] = C.c_void_p(flag.data_ptr())
+            check(c.fn(*args))
+            add_pending_flag(flag, ValueError(SCE_ERROR))
+        else:
+            check(c.fn(*args))
+        while on_ready is not None and ti < len(ends) and ends[ti] == k + 1:
+            on_ready(tops[ti])
+            ti += 1
+    while on_ready is not None and ti < len(tops):
+        on_ready(tops[ti])
+        ti += 1
+    stats["replays"] += 1
+    return True
+
+
+def lookup(sig):
+    """(tape | None, should_record)."""
+    tp = _tapes.get(sig)
+    if tp:
+        return tp, False
+    if tp is False:
+        return None, False
+    n = _seen.get(sig, 0) + 1
+    if len(_seen) > 4 * MAX_TAPES:
+        _seen.clear()
+    _seen[sig] = n
+    return None, n >= RECORD_AT
+
+
+def store(sig, tape):
+    if len(_tapes) >= MAX_TAPES:
+        _tapes.clear()
+    _tapes[sig] = tape if tape is not None else False
+    stats["records" if tape is not None else "rejected"] += 1
+
+
+def clear():
+    _seen.clear()
+    _tapes.clear()

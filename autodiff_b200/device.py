@@ -46,6 +46,7 @@ def _ensure_init():
 
 
 _stream = None
+_alloc_hook = None     # set by core/tape.py while a recording evaluation runs: hook(base tensor) for every DeviceArray.empty
 
 
 def stream_ptr():
@@ -113,6 +114,8 @@ class DeviceArray:
             n = shape[0] if shape else 1
             strides = _dense_strides(shape)
         base = t.empty(max(int(n), 2), dtype=t.float64, device="cuda")
+        if _alloc_hook is not None:
+            _alloc_hook(base)
         return DeviceArray(base, 0, shape, strides)
 
     @staticmethod
@@ -369,7 +372,7 @@ def copy_device(src, dst):
     code[1].op = _lib.EW_STORE_OUT; code[1].arg = 0
     tin = (_lib.Tensor * 1)(src.tensor())
     tout = (_lib.Tensor * 1)(dst.tensor())
-    _lib.check(_lib.lib().adb_ewise(code, 2, 1, tin, 1, tout, C.c_void_p(stream_ptr())))
+    _lib.call("adb_ewise", code, 2, 1, tin, 1, tout, C.c_void_p(stream_ptr()))
 
 
 def fill_device(dst, value):
@@ -377,7 +380,7 @@ def fill_device(dst, value):
     code[0].op = _lib.EW_LOAD | _lib.SRC_IMM; code[0].imm = float(value)
     code[1].op = _lib.EW_STORE_OUT; code[1].arg = 0
     tout = (_lib.Tensor * 1)(dst.tensor())
-    _lib.check(_lib.lib().adb_ewise(code, 2, 0, None, 1, tout, C.c_void_p(stream_ptr())))
+    _lib.call("adb_ewise", code, 2, 0, None, 1, tout, C.c_void_p(stream_ptr()))
 
 
 def to_host(d, pinned=True):

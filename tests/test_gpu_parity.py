@@ -488,3 +488,94 @@ def test_eval_many_pipelined_matches_sequential(ad):
     again = ad.eval_many(nodes)            # memoised
     for g, w in zip(again, want):
         assert np.array_equal(np.asarray(g), w)
+
+
+# ------------------------------------------------------------------------------------- launch tapes (core/tape.py)
+def _tape_graphs(ad, seed):
+    """A few graph families, rebuilt from scratch with fresh data for every seed (same structure, new values)."""
+    from autodiff_b200 import workloads as wl
+    rng = np.random.default_rng(seed)
+    out = {}
+    # MLP training graph (NN macro: Concat + Slice grads, ReLU, SoftmaxCE) - weights are shared across seeds like a real loop
+    x, lab = rng.random((32, 20)), np.eye(7)[rng.integers(0, 7, 32)]
+    w1, w2 = rng.standard_normal((21, 16)) * 0.1, rng.standard_normal((17, 7)) * 0.1
+    X, L, W1, W2 = ad.Variable(x, name="x"), ad.Variable(lab, name="l"), ad.Variable(w1, name="w1"), ad.Variable(w2, name="w2")
+    ones = ad.ConstFill((32, 1), 1.0)
+    h = ad.ReLU(ad.Concat(X, ones, axis=1) @ W1)
+    logits = ad.Concat(h, ad.ConstFill((32, 1), 1.0), axis=1) @ W2
+    cost = ad.Einsum("i->", ad.SoftmaxCEWithLogits(labels=L, logits=logits)) / 32
+    out["mlp"] = ad.grad(cost, [W1, W2]) + [cost]
+    # second-order char-rnn (Tanh macro, Softmax grads, thousands of Add/Mul nodes)
+    H, V, B, T = 12, 9, 6, 5
+    prm = [ad.Variable(p, name="p%d" % i) for i, p in enumerate(wl.char_rnn_params(rng, H, V))]
+    oh = np.eye(V)[rng.integers(0, V, (B, T))]
+    loss = wl.char_rnn(ad, oh, *prm)
+    g = ad.grad(loss, [prm[0]])[0]
+    out["rnn2"] = [ad.grad(g, [prm[0]])[0], g, loss]
+    # conv net
+    xs = rng.standard_normal((3, 12, 12, 2)); ys = np.eye(4)[rng.integers(0, 4, 3)]
+    P = [ad.Variable(p, name="c%d" % i) for i, p in enumerate(wl.conv_net_params(rng, c_in=2, c1=3, c2=4, k=3, hw=12, classes=4))]
+    closs = wl.conv_net(ad, ad.Variable(xs, name="x"), ad.Variable(ys, name="y"), *P)
+    out["conv"] = ad.grad(closs, P) + [closs]
+    # reshapes / pads / slices / reductions / scalar operands
+    a, b = rng.standard_normal((6, 10)), rng.random((6, 10)) + 0.5
+    A, Bv = ad.Variable(a, name="a"), ad.Variable(b, name="b")
+    out["misc"] = [ad.Pad(A, ((1, 2), (0, 3)), 0.5) * 2.0, ad.Reshape(A * Bv, (10, 6)), A[1:5, ::2] + 1.0, ad.Einsum("ab->b", A / Bv),
+                   ad.Einsum("ab,->ab", A, 3.0), ad.FrobeniusNorm(A, Bv), ad.ReduceSumKeepDims(ad.Exp(A), axes=[1]), ad.Transpose(A) @ Bv]
+    return out
+
+
+def test_launch_tapes_replay_bitwise(ad):
+    """From the 3rd evaluation of a structure on, evaluate_many replays a launch tape: results must equal the normal
+    planner/executor path bit for bit, for fresh data and fresh graph objects every time."""
+    from autodiff_b200.core import engine, tape
+    assert tape.ENABLED
+    tape.clear()
+    want = {}
+    tape.ENABLED = False
+    try:
+        for seed in range(5):
+            for name, nodes in _tape_graphs(ad, seed).items():
+                engine.evaluate_many(nodes)
+                want[(seed, name)] = [np.asarray(n()) for n in nodes]
+    finally:
+        tape.ENABLED = True
+    before = dict(tape.stats)
+    for seed in range(5):
+        for name, nodes in _tape_graphs(ad, seed).items():
+            engine.evaluate_many(nodes)
+            got = [np.asarray(n()) for n in nodes]
+            for k, (g, w) in enumerate(zip(got, want[(seed, name)])):
+                assert g.shape == w.shape, (seed, name, k)
+                assert np.array_equal(g, w), "seed %d graph %s output %d differs under the tape" % (seed, name, k)
+    assert tape.stats["records"] - before["records"] >= 4, tape.stats
+    assert tape.stats["replays"] - before["replays"] >= 12, tape.stats
+
+
+def test_launch_tapes_intermediates_flags_and_callbacks(ad):
+    from autodiff_b200.core import engine, tape
+    tape.clear()
+    rng = np.random.default_rng(5)
+
+    def build(bad=False):
+        z = rng.standard_normal((8, 5)); lab = np.eye(5)[rng.integers(0, 5, 8)]
+        if bad:
+            lab[3] *= 2.0
+        Z, Lb = ad.Variable(z, name="z"), ad.Variable(lab, name="l")
+        mid = ad.Exp(Z * 0.5)
+        sce = ad.SoftmaxCEWithLogits(labels=Lb, logits=mid + Z)
+        return z, lab, mid, sce, ad.Einsum("i->", sce)
+    for i in range(4):
+        z, lab, mid, sce, tot = build()
+        fired = []
+        engine.evaluate_many([tot, sce], on_ready=lambda n: fired.append(n))
+        assert fired == [tot, sce]
+        ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab), logits=onp.Variable(np.exp(z * 0.5) + z))()
+        check(sce(), ref)
+        check(tot(), ref.sum())
+        check(mid(), np.exp(z * 0.5))          # an intermediate of a replayed graph is still available
+    assert tape.stats["replays"] >= 2
+    z, lab, mid, sce, tot = build(bad=True)      # the deferred label check still fires on the replay path
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        engine.evaluate_many([tot])
+        tot()
