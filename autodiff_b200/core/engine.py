@@ -182,7 +182,10 @@ def evaluate_many(tops, on_ready=None):
             if rec is not None:
                 tape._recorder, _lib._call_hook, _device._alloc_hook = None, None, None
         if rec is not None:
-            tape.store(sig, tape.build_tape(rec, scanned[0], scanned[1], len(tops)))
+            built = tape.build_tape(rec, scanned[0], scanned[1], len(tops))
+            tape.store(sig, built)
+            if built is not None and tape.SELF_CHECK:
+                tape.self_check(built, scanned[0], scanned[1], tops, _materialise_leaf, add_pending_flag)
 
 
 def _materialise_leaf(node):

@@ -32,6 +32,11 @@ from .node import ConstFill, Node, Variable
 
 ENABLED = os.environ.get("ADB_TAPE", "1") != "0"
 RECORD_AT = 2            # record on the 2nd sighting of a structure, replay from the 3rd
+# ADB_TAPE_SELFCHECK=1 (test-suite stress mode): record on the FIRST sighting, then immediately replay the fresh tape onto
+# the same graph and require every materialised node to come out bit-identical to the recorded run.
+SELF_CHECK = os.environ.get("ADB_TAPE_SELFCHECK", "0") == "1"
+if SELF_CHECK:
+    RECORD_AT = 1
 MAX_TAPES = 64
 SCE_ERROR = "Labels must be a valid probability distribution!"
 
@@ -320,6 +325,28 @@ def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
         ti += 1
     stats["replays"] += 1
     return True
+
+
+def self_check(tape, order, leaves, tops, dev_of, add_pending_flag):
+    """Replays a freshly recorded tape onto the graph it was recorded from and compares every node value bitwise."""
+    from ..device import to_host
+    want = {}
+    for i, n in enumerate(order):
+        if leaves[i] is None and n._dev is not None:
+            want[i] = (to_host(n._dev, pinned=False), n._dev)
+    for i in want:
+        order[i]._dev = None
+    if not replay(tape, order, leaves, tops, dev_of, add_pending_flag, None):
+        for i, (_, d) in want.items():
+            order[i]._dev = d
+        return
+    for i, (host, d) in want.items():
+        n = order[i]
+        got = to_host(n._dev, pinned=False) if n._dev is not None else None
+        if got is None or got.shape != host.shape or not np.array_equal(got, host, equal_nan=True):
+            raise AssertionError("launch tape self-check: node %d (%s %s) differs between the recorded run and its replay"
+                                 % (i, type(n).__name__, getattr(n, "name", "")))
+    stats["self_checks"] = stats.get("self_checks", 0) + 1
 
 
 def lookup(sig):

@@ -33,6 +33,12 @@ def pytest_collection_modifyitems(config, items):
 def pytest_sessionfinish(session, exitstatus):
     """ADB_EW_STATS=<file>: dump which elementwise programs the GPU tests ran (tools/gen_ewise_catalog.py --merge)."""
     import os
+    if os.environ.get("ADB_TAPE_SELFCHECK") == "1":
+        try:
+            from autodiff_b200.core import tape
+            print("\nlaunch-tape self-check: %s" % (tape.stats,))
+        except Exception:
+            pass
     path = os.environ.get("ADB_EW_STATS")
     if path:
         try:

@@ -529,7 +529,8 @@ def test_launch_tapes_replay_bitwise(ad):
     """From the 3rd evaluation of a structure on, evaluate_many replays a launch tape: results must equal the normal
     planner/executor path bit for bit, for fresh data and fresh graph objects every time."""
     from autodiff_b200.core import engine, tape
-    assert tape.ENABLED
+    if not tape.ENABLED:
+        pytest.skip("ADB_TAPE=0")
     tape.clear()
     want = {}
     tape.ENABLED = False
@@ -554,6 +555,8 @@ def test_launch_tapes_replay_bitwise(ad):
 
 def test_launch_tapes_intermediates_flags_and_callbacks(ad):
     from autodiff_b200.core import engine, tape
+    if not tape.ENABLED:
+        pytest.skip("ADB_TAPE=0")
     tape.clear()
     rng = np.random.default_rng(5)
 
