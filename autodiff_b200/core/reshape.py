@@ -144,6 +144,8 @@ class Slice(Node):
     def _partial_derivative(self, wrt, previous_grad):
         # The reference evaluates previous_grad HERE, at graph-build time, and returns a constant ndarray
         # (reshape.py:96-102).  Same eagerness, but the scatter runs on the device and the constant stays in HBM.
+        if self.node == wrt and lazy_slice_grad.enabled:
+            return SliceScatter(previous_grad, tuple(wrt.shape), self.slice_val)     # a real graph node
         if self.node == wrt:
             g = DeviceArray.empty(tuple(wrt.shape))
             fill_device(g, 0.0)
@@ -151,6 +153,47 @@ class Slice(Node):
             copy_device(pg, g.getitem(self.slice_val))
             return Variable(g, name="Slice grad")
         return 0
+
+
+class SliceScatter(Node):
+    """zeros(shape) with [slice_val] = node: the gradient of `Slice` as a GRAPH NODE.  The
+    reference evaluates that gradient eagerly into a constant (reshape.py:96-102), which makes second-order gradients
+    through Slice / Concat / NN silently constant; with `ad.lazy_slice_grad(True)` this node is used instead and
+    gradients of any order through slicing are correct.  Its own derivative is the Slice of the incoming gradient."""
+
+    def __init__(self, node, shape, slice_val, name="SliceScatter"):
+        super().__init__([node], name)
+        self.node = self.children[0]
+        self.shape = tuple(int(s) for s in shape)
+        self.slice_val = tuple(slice_val) if isinstance(slice_val, list) else slice_val
+
+    def _eval_device(self):
+        g = DeviceArray.empty(self.shape)
+        fill_device(g, 0.0)
+        copy_device(dev(self.node), g.getitem(self.slice_val))
+        return g
+
+    def _partial_derivative(self, wrt, previous_grad):
+        if self.node == wrt:
+            return Reshape(previous_grad, self.shape)[self.slice_val]
+        return 0
+
+
+class lazy_slice_grad:
+    """`ad.lazy_slice_grad(True)` (or `with ad.lazy_slice_grad(True): ...`) makes Slice's gradient a graph node instead
+    of the reference's eagerly evaluated constant.  Default off: bug-for-bug parity with the reference."""
+    enabled = False
+
+    def __init__(self, on=True):
+        self.prev = lazy_slice_grad.enabled
+        lazy_slice_grad.enabled = bool(on)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        lazy_slice_grad.enabled = self.prev
+        return False
 
 
 class Pad(Node):
@@ -199,4 +242,5 @@ from . import tape as _tape  # noqa: E402
 _tape.register(Concat, "axis")
 _tape.register(Reshape, "shape")
 _tape.register(Slice, "slice_val")
+_tape.register(SliceScatter, "shape", "slice_val")
 _tape.register(Pad, "_pairs", "constant_values")

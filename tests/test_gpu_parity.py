@@ -582,3 +582,26 @@ def test_launch_tapes_intermediates_flags_and_callbacks(ad):
     with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
         engine.evaluate_many([tot])
         tot()
+
+
+def test_lazy_slice_gradient_is_differentiable(ad):
+    """with ad.lazy_slice_grad(True) the gradient of Slice is a graph node, so second-order gradients
+    through slicing are right (the reference's eager constant makes them 0); the default stays reference-compatible."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((7, 5))
+
+    def second(lazy):
+        X = ad.Variable(x, name="x")
+        with ad.lazy_slice_grad(lazy):
+            s = X[1:6, ::2]
+            f = ad.Einsum("ab->", s * s * s)
+            g = ad.grad(f, [X])[0]
+            h = ad.grad(ad.Einsum("ab->", g * g), [X])[0]       # d/dx sum((3x^2)^2 on the slice) = 36 x^3 on the slice
+        return np.asarray(g()), np.broadcast_to(np.asarray(h()), x.shape)
+    mask = np.zeros_like(x); mask[1:6, ::2] = 1.0
+    g, h = second(True)
+    check(g, 3 * x * x * mask)
+    check(h, 36 * x ** 3 * mask)
+    g0, h0 = second(False)
+    check(g0, 3 * x * x * mask)
+    assert not np.allclose(h0, 36 * x ** 3 * mask)                # the reference quirk: the first gradient was a constant
