@@ -765,15 +765,24 @@ __device__ __forceinline__ double block_reduce_max(double v, double* sm) {
     return t;
 }
 
-// K quads per thread, NT threads per CTA: cols <= NT * 4 * K.  Wide rows use 512 threads so that 32 warps per SM
-// stay resident (the exp() chain is FP64-pipe work that has to overlap the next row's loads).
+// K quads per thread, NT threads per CTA: cols <= NT * 4 * K.  Single pass ("online" log-sum-exp): every thread
+// reduces its own elements to (max m, sum exp(z - m), sum l, sum l*z); pairs (m, s) combine as
+// (M, s1*exp(m1-M) + s2*exp(m2-M)) with M = max(m1, m2) through warp shuffles and ONE shared-memory exchange, so a
+// row costs one block barrier instead of four dependent phases.  out = -(sum l*z - lse * sum l), the reference's
+// -sum(l*z - l*lse) re-associated (error ~1e-16 of the terms; parity bar 1e-12).
+__device__ __forceinline__ void lse_combine(double& m, double& s, double m2, double s2) {
+    const double M = fmax(m, m2);
+    if (M == -INFINITY) { s = s + s2; m = M; return; }     // both empty so far (or all -inf: numpy gives nan, see below)
+    s = s * exp(m - M) + s2 * exp(m2 - M);
+    m = M;
+}
+
 template <int K, int NT>
 __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
                                                              long long z_sr, double* __restrict__ out, long long o_s, long long rows,
                                                              unsigned cols, int* __restrict__ flag) {
     constexpr int NW = NT / 32;
-    __shared__ double sm[NW];
-    __shared__ int sm_nan;
+    __shared__ double sm[4][NW];
     const long long r = blockIdx.x;
     const double* z = logits + r * z_sr;
     const double* l = labels + r * l_sr;
@@ -787,49 +796,63 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                zq[k].v[e] = c + e < cols ? __ldg(z + c + e) : -INFINITY;   // exp(-inf - mx) = 0, label 0: no contribution
+                zq[k].v[e] = c + e < cols ? __ldg(z + c + e) : -INFINITY;   // neutral: never the max, exp() = 0, label 0
                 lq[k].v[e] = c + e < cols ? __ldg(l + c + e) : 0.0;
             }
         }
     }
-    if (threadIdx.x == 0) sm_nan = 0;
-    double mx = -INFINITY;
-    bool nan_seen = false;
+    double m = -INFINITY;
+    bool has_nan = false;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { nan_seen |= (zq[k].v[e] != zq[k].v[e]); mx = fmax(mx, zq[k].v[e]); }
+        for (int e = 0; e < 4; ++e) { m = fmax(m, zq[k].v[e]); has_nan |= zq[k].v[e] != zq[k].v[e]; }
     }
-    mx = block_reduce_max<NW>(mx, sm);
-    if (nan_seen) sm_nan = 1;
-    __syncthreads();
-    if (sm_nan) mx = NAN;      // np.max propagates NaN
-    double se = 0.0, lsum = 0.0;
+    // the WARP's max first (plain fmax shuffles), so that each element costs exactly one exp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    double se = 0.0, lsum = 0.0, dot = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
-            if (c < cols) se += exp(zq[k].v[e] - mx);
+            if (c < cols) {
+                if (m != -INFINITY) se += exp(zq[k].v[e] - m);
+                dot += lq[k].v[e] * zq[k].v[e];
+            }
             lsum += lq[k].v[e];
         }
     }
-    se = block_reduce_sum<NW>(se, sm);
-    lsum = block_reduce_sum<NW>(lsum, sm);
-    const double lse = mx + log(se);
-    double sdot = 0.0;
+    if (has_nan) se = NAN;                     // np.max propagates NaN (fmax does not)
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
-            if (c < cols) sdot += lq[k].v[e] * zq[k].v[e] - lq[k].v[e] * lse;
-        }
+    for (int off = 16; off > 0; off >>= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, off);
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        dot += __shfl_xor_sync(0xffffffffu, dot, off);
     }
-    sdot = block_reduce_sum<NW>(sdot, sm);
-    if (threadIdx.x == 0) {
-        out[r * o_s] = -sdot;
-        if (!(fabs(lsum - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        sm[0][w] = m; sm[1][w] = se; sm[2][w] = lsum; sm[3][w] = dot;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                    // warp 0 combines the NW per-warp results (log-sum-exp pairs rescaled)
+        const int w = threadIdx.x;
+        double M = w < NW ? sm[0][w] : -INFINITY, S = w < NW ? sm[1][w] : 0.0;
+        double L = w < NW ? sm[2][w] : 0.0, D = w < NW ? sm[3][w] : 0.0;
+#pragma unroll
+        for (int off = NW / 2; off > 0; off >>= 1) {
+            const double m2 = __shfl_xor_sync(0xffffffffu, M, off), s2 = __shfl_xor_sync(0xffffffffu, S, off);
+            lse_combine(M, S, m2, s2);
+            L += __shfl_xor_sync(0xffffffffu, L, off);
+            D += __shfl_xor_sync(0xffffffffu, D, off);
+        }
+        if (w == 0) {
+            if (M == -INFINITY) S = NAN;       // a row of -inf: numpy computes exp(-inf - -inf) = nan
+            const double lse = M + log(S);
+            out[r * o_s] = -(D - lse * L);
+            if (!(fabs(L - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+        }
     }
 }
 

@@ -605,3 +605,22 @@ def test_lazy_slice_gradient_is_differentiable(ad):
     g0, h0 = second(False)
     check(g0, 3 * x * x * mask)
     assert not np.allclose(h0, 36 * x ** 3 * mask)                # the reference quirk: the first gradient was a constant
+
+
+def test_empty_and_degenerate_shapes(ad):
+    """Zero-extent and single-element tensors through every kernel family (numpy semantics: empty sums are 0)."""
+    z = np.zeros((0, 5)); o = np.ones((3, 0)); s = np.array([[2.5]])
+    check(ad.Einsum("ab->b", ad.Variable(z))(), z.sum(0))
+    check(ad.Einsum("ab->a", ad.Variable(o))(), o.sum(1))
+    check(ad.Einsum("ab->", ad.Variable(z))(), 0.0)
+    assert (ad.Variable(z) + ad.Variable(z))().shape == (0, 5)
+    assert ad.ReLU(ad.Variable(o))().shape == (3, 0)
+    assert (ad.Variable(np.ones((4, 0))) @ ad.Variable(np.ones((0, 6))))().shape == (4, 6)
+    check((ad.Variable(np.ones((4, 0))) @ ad.Variable(np.ones((0, 6))))(), np.zeros((4, 6)))
+    assert (ad.Variable(np.ones((0, 3))) @ ad.Variable(np.ones((3, 6))))().shape == (0, 6)
+    check(ad.Einsum("ab,bc->ac", ad.Variable(s), ad.Variable(s))(), s @ s)
+    check(ad.Tanh(ad.Variable(s))(), onp.Tanh(onp.Variable(s))())
+    check(ad.Einsum("ab->", ad.Variable(s))(), 2.5)
+    check(ad.ReduceSumKeepDims(ad.Variable(np.arange(6.0).reshape(1, 6)), axes=[0, 1])(), np.array([[15.0]]))
+    check(ad.Concat(ad.Variable(np.ones((2, 0))), ad.Variable(np.full((2, 3), 7.0)), axis=1)(), np.full((2, 3), 7.0))
+    check(ad.FrobeniusNorm(ad.Variable(z))(), 0.0)
