@@ -57,6 +57,7 @@ struct EwParams {
     const double* in[ADB_EW_MAX_IN];
     double* out[ADB_EW_MAX_OUT];
     unsigned in_mode, out_mode;  // 2 bits per tensor: how a full quad is accessed (EW_BCAST / EW_V256 / EW_V128 / EW_SCALAR)
+    unsigned off32;              // every element offset of every tensor fits 31 bits and no stride is negative: 32-bit index math
     adb_ew_instr code[ADB_EW_MAX_INSTR];
 };
 
@@ -75,7 +76,13 @@ __device__ __forceinline__ void stg256(double* p, const Vec& a) {
 }
 
 template <int ND>
-__device__ __forceinline__ long long ew_offset(const long long* stride, const unsigned (&idx)[ND]) {
+__device__ __forceinline__ long long ew_offset(const EwParams& P, const long long* stride, const unsigned (&idx)[ND]) {
+    if (ND > 1 && P.off32) {     // (uniform branch) one 32-bit IMAD per dim instead of a 64-bit multiply-add chain
+        unsigned off = 0;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) off += idx[k] * (unsigned)stride[k];
+        return (long long)off;
+    }
     long long base = 0;
 #pragma unroll
     for (int k = 0; k < ND; ++k) base += (long long)idx[k] * stride[k];
@@ -85,7 +92,7 @@ __device__ __forceinline__ long long ew_offset(const long long* stride, const un
 template <int ND>
 __device__ __forceinline__ Vec load_in(const EwParams& P, int i, const unsigned (&idx)[ND], unsigned nvalid) {
     Vec r;
-    const double* p = P.in[i] + ew_offset<ND>(P.in_stride[i], idx);
+    const double* p = P.in[i] + ew_offset<ND>(P, P.in_stride[i], idx);
     const unsigned mode = (P.in_mode >> (2 * i)) & 3u;
     if (mode == EW_BCAST) {
         const double x = __ldg(p);
@@ -105,7 +112,7 @@ __device__ __forceinline__ Vec load_in(const EwParams& P, int i, const unsigned 
 
 template <int ND>
 __device__ __forceinline__ void store_out(const EwParams& P, int j, const unsigned (&idx)[ND], unsigned nvalid, const Vec& a) {
-    double* p = P.out[j] + ew_offset<ND>(P.out_stride[j], idx);
+    double* p = P.out[j] + ew_offset<ND>(P, P.out_stride[j], idx);
     const unsigned mode = (P.out_mode >> (2 * j)) & 3u;
     if (nvalid == EW_V && mode == EW_V256) {
         stg256(p, a);
