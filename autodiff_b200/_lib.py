@@ -58,6 +58,7 @@ PROTOTYPES = {
     "adb_ewise": (C.c_int, [C.POINTER(EwInstr), C.c_int, C.c_int, C.POINTER(Tensor), C.c_int, C.POINTER(Tensor), C.c_void_p]),
     "adb_ewise_stats": (C.c_int, [C.c_char_p, C.c_size_t]),
     "adb_ewise_force_interpreter": (C.c_int, [C.c_int]),
+    "adb_ewise_set_piece_limit": (C.c_int, [C.c_longlong]),
     "adb_einsum": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "adb_einsum_describe": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.c_char_p, C.c_size_t]),
     "adb_reduce_sum": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),

@@ -161,7 +161,7 @@ def evaluate_many(tops, on_ready=None):
             scanned = tape.scan(tops, scalar_of, _has_value, _is_device_node)
             if scanned is not None and any(l is None for l in scanned[1]):      # (a graph of leaves only has nothing to replay)
                 order, leaves, sig = scanned
-                sig = (fusion_enabled, len(tops)) + sig
+                sig = (fusion_enabled, Node.epsilon, len(tops)) + sig
                 tp, should_record = tape.lookup(sig)
                 if tp is not None and tape.replay(tp, order, leaves, tops, _materialise_leaf, add_pending_flag, on_ready):
                     return

@@ -247,12 +247,19 @@ class _PinnedBlock:
         self.ptr, self.cap = ptr, cap
 
     def __del__(self):
+        global _pinned_pooled
         try:
-            _pinned_free.setdefault(self.cap, []).append(self.ptr)
+            if _pinned_pooled + self.cap <= _PINNED_POOL_MAX:
+                _pinned_free.setdefault(self.cap, []).append(self.ptr)
+                _pinned_pooled += self.cap
+            else:
+                _lib.lib().adb_host_free(C.c_void_p(self.ptr))
         except Exception:      # interpreter shutdown
             pass
 
 
+_pinned_pooled = 0                 # bytes currently parked in the pool
+_PINNED_POOL_MAX = 48 << 30        # beyond this, blocks go back to the driver instead of the pool
 _pinned_free = {}      # capacity -> [host pointers]; page-locked memory is expensive to create (~0.3 s/GiB), so it is recycled
 _PINNED_GRAIN = 1 << 21
 
@@ -265,9 +272,11 @@ def pinned_empty(shape, dtype=np.float64):
     if not torch().cuda.is_available():
         return np.empty(shape, dtype=dtype)
     cap = (nbytes + _PINNED_GRAIN - 1) // _PINNED_GRAIN * _PINNED_GRAIN
+    global _pinned_pooled
     free = _pinned_free.get(cap)
     if free:
         ptr = free.pop()
+        _pinned_pooled -= cap
     else:
         out = C.c_void_p()
         _lib.check(_lib.lib().adb_host_alloc(C.byref(out), cap))

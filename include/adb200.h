@@ -125,6 +125,8 @@ ADB_API int adb_ewise(const adb_ew_instr* code, int n_instr, int n_in, const adb
  * adb_ewise_force_interpreter(1) disables the catalogue (A/B measurements, parity tests of both paths). */
 ADB_API int adb_ewise_stats(char* buf, size_t buflen);
 ADB_API int adb_ewise_force_interpreter(int on);
+/* test hook: quads per launch before an iteration space is split on the host (0 = the real limit, 2^31 - 1) */
+ADB_API int adb_ewise_set_piece_limit(long long quads);
 
 /* ---- einsum: replaces np.einsum(self.op_str, *arr) at reference autodiff/core/ops.py:180 ----------
  *  op_str uses single letters [a-zA-Z] with an explicit "->" (the host expands "..." first, mirroring

@@ -624,3 +624,22 @@ def test_empty_and_degenerate_shapes(ad):
     check(ad.ReduceSumKeepDims(ad.Variable(np.arange(6.0).reshape(1, 6)), axes=[0, 1])(), np.array([[15.0]]))
     check(ad.Concat(ad.Variable(np.ones((2, 0))), ad.Variable(np.full((2, 3), 7.0)), axis=1)(), np.full((2, 3), 7.0))
     check(ad.FrobeniusNorm(ad.Variable(z))(), 0.0)
+
+
+def test_elementwise_iteration_space_splitting(ad):
+    """Iteration spaces beyond 2^31 quads are halved on the host until they fit; exercised here by lowering the limit."""
+    from autodiff_b200 import _lib
+    rng = np.random.default_rng(8)
+    x, y, b = rng.standard_normal((37, 50, 21)), rng.standard_normal((37, 50, 21)), rng.standard_normal((50, 1))
+    flat = rng.standard_normal(100003)
+    try:
+        _lib.check(_lib.lib().adb_ewise_set_piece_limit(257))
+        got = [(ad.Variable(x) * ad.Variable(y) + ad.Variable(b))(), ad.Tanh(ad.Variable(flat))(), ad.Transpose(ad.Variable(x[0])) @ ad.Variable(y[0]),
+               ad.Einsum("abc,bo->abc", ad.Variable(x), ad.Variable(b))()]
+        got[2] = got[2]()
+    finally:
+        _lib.check(_lib.lib().adb_ewise_set_piece_limit(0))
+    check(got[0], x * y + b)
+    check(got[1], onp.Tanh(onp.Variable(flat))())
+    check(got[2], x[0].T @ y[0])
+    check(got[3], x * b)
