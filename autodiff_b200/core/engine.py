@@ -204,20 +204,24 @@ def evaluate(top):
 
 # ------------------------------------------------------------------------------------------- pipelined host API
 _side_streams = None
+pipeline_trace = None             # tools/e2e_trace.py sets this to a list: (label, timing event) pairs of one eval_many call
 PIPELINE_MIN_BYTES = 1 << 20      # results smaller than this are read back by the plain synchronous path at the end
+HEAVY_FLOPS = 2e11                # an output whose sub-graph contracts more than this (~6 ms of DMMA) is "heavy"
 
 
 def _streams():
+    """(h2d, light compute [high priority], d2h for the main stream, d2h for the light stream)."""
     global _side_streams
     if _side_streams is None:
         t = torch()
-        _side_streams = (t.cuda.Stream(), t.cuda.Stream())
+        _side_streams = (t.cuda.Stream(), t.cuda.Stream(priority=-1), t.cuda.Stream(), t.cuda.Stream())
     return _side_streams
 
 
-def _host_leaves(top, seen):
-    """Leaves under `top` (within the not-yet-evaluated sub-DAG) whose host ndarray still has to be uploaded."""
-    out, stack = [], [top]
+def _survey(top):
+    """One walk of the not-yet-evaluated sub-DAG under `top`: (host leaves to upload, ids of all leaves that may be
+    uploaded asynchronously, ids of the interior nodes, rough contraction flops)."""
+    uploads, leaf_ids, interior, flops, seen, stack = [], [], set(), 0.0, set(), [top]
     while stack:
         n = stack.pop()
         if id(n) in seen:
@@ -226,63 +230,145 @@ def _host_leaves(top, seen):
         if isinstance(n, Variable):
             if isinstance(n, ConstFill) and n.fill is not None and n._host is None:
                 continue                       # never materialised: a one-element broadcast on the device
-            if n._dev is None and scalar_of(n) is None:
-                v = n._host if n._host is not None else n._value
-                if isinstance(v, np.ndarray) and v.size > 0:
-                    out.append((n, v))         # small leaves too: a synchronous upload would wait for every queued kernel
+            if scalar_of(n) is None:
+                leaf_ids.append(id(n))
+                if n._dev is None:
+                    v = n._host if n._host is not None else n._value
+                    if isinstance(v, np.ndarray) and v.size > 0:
+                        uploads.append((n, v))     # small leaves too: a synchronous upload would wait for every queued kernel
             continue
         if _has_value(n) or not _is_device_node(n):
             continue
+        interior.add(id(n))
+        ltd = getattr(n, "letter_to_dim", None)
+        if ltd:                                 # an einsum: 2 * product of all letter extents
+            f = 2.0
+            for dims in ltd.values():
+                for d in dims:
+                    f *= d
+            flops += f
         stack.extend(n.children)
-    return out
+    return uploads, leaf_ids, interior, flops
 
 
 def eval_many(tops):
     """`[t() for t in tops]` as ONE pipelined pass: returns the host values (and memoises them in `node.cached`, as
-    reference node.py:42-46 does), but the host->device copies of the leaves, the kernels, and the device->host
-    copies of the results run on three streams - uploads of later outputs' operands and downloads of earlier
-    outputs overlap the kernels in between.  Values are identical to evaluating the nodes one by one."""
+    reference node.py:42-46 does) while host->device copies of the leaves, kernels and device->host copies of the
+    results overlap:
+      * every leaf upload is queued up front on a copy stream, each output waits only for its own leaves;
+      * outputs that share no interior node are independent jobs; the cheap ones (several times cheaper than the heaviest job) run on
+        a HIGH-PRIORITY compute stream, so their kernels slip in between the CTAs of a long GEMM of another output
+        instead of queueing behind it, and their results start travelling back while that GEMM is still running;
+      * each compute stream has its own download stream, so a result that is ready never waits behind one that is not.
+    Values are identical to evaluating the nodes one by one (same kernels, same operands)."""
+    from .. import device as _device
+    from ..device import enqueue_download, to_device_async, use_stream
     tops = list(tops)
     t = torch()
-    from ..device import enqueue_download, to_device_async
-    h2d, d2h = _streams()
-    compute = t.cuda.current_stream()
+    h2d, light, d2h_main, d2h_light = _streams()
+    main = t.cuda.current_stream()
     pending = [x for x in tops if x._host is None]
     todo = [x for x in pending if x._dev is None]
-    # 1. queue every large leaf upload, in the order the outputs need them
-    seen, per_top, keep = set(), {}, []
-    start = t.cuda.Event()
-    start.record(compute)             # recycled allocator blocks may still be in use by kernels queued earlier
+    # 1. survey every output; queue every leaf upload in the order the outputs need them
+    tr = pipeline_trace
+    start = t.cuda.Event(enable_timing=tr is not None)
+    start.record(main)               # recycled allocator blocks may still be in use by kernels queued earlier
     h2d.wait_event(start)
+    if tr is not None:
+        tr.append(("start", start))
+    info, leaf_event, keep = {}, {}, []
     for x in todo:
-        evs = []
-        for leaf, value in _host_leaves(x, seen):
-            leaf._dev, staged = to_device_async(value, h2d)
-            keep.append(staged)
-            ev = t.cuda.Event()
-            ev.record(h2d)
-            evs.append(ev)
-        per_top[id(x)] = evs
-    # 2. kernels per output; each result's download is queued behind its own kernels only
-    plan = _plan(todo)
+        uploads, leaf_ids, interior, flops = _survey(x)
+        for leaf, value in uploads:
+            if leaf._dev is None:
+                leaf._dev, staged = to_device_async(value, h2d)
+                keep.append(staged)
+                ev = t.cuda.Event(enable_timing=tr is not None)
+                ev.record(h2d)
+                leaf_event[id(leaf)] = ev
+                if tr is not None:
+                    tr.append(("uploaded %s %s" % (leaf.name, value.shape), ev))
+        info[id(x)] = (leaf_ids, interior, flops)
+    # 2. independent jobs = connected components over shared interior nodes
+    comp = list(range(len(todo)))
+
+    def find(i):
+        while comp[i] != i:
+            comp[i] = comp[comp[i]]
+            i = comp[i]
+        return i
+    owner = {}
+    for i, x in enumerate(todo):
+        for nid in info[id(x)][1]:
+            j = owner.setdefault(nid, i)
+            if j != i:
+                comp[find(i)] = find(j)
+    groups = {}
+    for i, x in enumerate(todo):
+        groups.setdefault(find(i), []).append(x)
+    heaviest = max([sum(info[id(x)][2] for x in g) for g in groups.values()] or [0.0])
+    plans = {}
+    stream_of = {}
+    for g in groups.values():
+        plan = _plan(g)
+        # light = a job several times cheaper than the heaviest one, when that one is long enough to be worth dodging
+        is_light = heaviest >= HEAVY_FLOPS and len(groups) > 1 and sum(info[id(x)][2] for x in g) < 0.3 * heaviest
+        for x in g:
+            plans[id(x)] = plan
+            stream_of[id(x)] = light if is_light else main
+    # 3. kernels per output on its job's stream; each result's download is queued behind its own kernels only
     results = {}
-    for x in pending:
-        for ev in per_top.get(id(x), ()):
-            compute.wait_event(ev)
-        if x._dev is None:
-            _execute(x, plan)
-        if x._dev is None:            # foreign (numpy) node: already has its host value
-            continue
-        d = x._dev
-        if d.size * 8 >= PIPELINE_MIN_BYTES:
-            done = t.cuda.Event()
-            done.record(compute)
-            d2h.wait_event(done)
-            host = enqueue_download(d, d2h)
-            if host is not None:
-                results[id(x)] = host
-    d2h.synchronize()
-    compute.synchronize()
+    used_light = False
+    try:
+        for x in pending:
+            cs = stream_of.get(id(x), main)
+            if x._dev is None:
+                if cs is light:
+                    if not used_light:
+                        light.wait_event(start)
+                        used_light = True
+                    use_stream(light)
+                    _device._alloc_hook = lambda base: base.record_stream(main)   # values outlive this call on `main`
+                    ctx = t.cuda.stream(light)
+                else:
+                    ctx = None
+                try:
+                    if ctx is not None:
+                        ctx.__enter__()
+                    for lid in info[id(x)][0]:
+                        ev = leaf_event.get(lid)
+                        if ev is not None:
+                            cs.wait_event(ev)
+                    _execute(x, plans[id(x)])
+                finally:
+                    if ctx is not None:
+                        ctx.__exit__(None, None, None)
+                        use_stream(main)
+                        _device._alloc_hook = None
+            if x._dev is None:            # foreign (numpy) node: already has its host value
+                continue
+            d = x._dev
+            if d.size * 8 >= PIPELINE_MIN_BYTES:
+                done = t.cuda.Event(enable_timing=tr is not None)
+                done.record(cs)
+                dl = d2h_light if cs is light else d2h_main
+                dl.wait_event(done)
+                host = enqueue_download(d, dl)
+                if host is not None:
+                    results[id(x)] = host
+                if tr is not None:
+                    back = t.cuda.Event(enable_timing=True)
+                    back.record(dl)
+                    tr.append(("computed %s %s on %s" % (x.name[:24], d.shape, "light" if cs is light else "main"), done))
+                    tr.append(("downloaded %s" % x.name[:24], back))
+    finally:
+        use_stream(main)
+        _device._alloc_hook = None
+    d2h_main.synchronize()
+    d2h_light.synchronize()
+    if used_light:
+        light.synchronize()
+    main.synchronize()
     check_pending_flags()
     del keep
     out = []

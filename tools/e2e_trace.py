@@ -31,6 +31,14 @@ for i in range(4):
     del hosts
     print("step %d: build %.1f ms, eval_many %.1f ms" % (i, b * 1e3, e * 1e3), flush=True)
 
+engine.pipeline_trace = []
+step()
+torch.cuda.synchronize()
+t0 = engine.pipeline_trace[0][1]
+for label, ev in engine.pipeline_trace[1:]:
+    print("  %7.1f ms  %s" % (t0.elapsed_time(ev), label))
+engine.pipeline_trace = None
+
 # raw copy speeds
 x = host_inputs["C2c"][0]
 d = ad.to_device(x)
