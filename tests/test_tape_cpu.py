@@ -1,0 +1,81 @@
+"""Host-side logic of the launch tapes (autodiff_b200/core/tape.py) that needs no GPU: the structural signature must be
+equal for isomorphic graphs and differ whenever the kernels or their wiring would differ."""
+import numpy as np
+
+import autodiff_b200 as ad
+from autodiff_b200.core import engine, tape
+
+
+def _sig(tops):
+    r = tape.scan(list(tops), engine.scalar_of, engine._has_value, engine._is_device_node)
+    return None if r is None else r[2]
+
+
+def _mlp(seed, scale=2.0, share=True, width=5):
+    rng = np.random.default_rng(seed)
+    x = ad.Variable(rng.standard_normal((4, width)), name="x")
+    w = ad.Variable(rng.standard_normal((width, 3)), name="w")
+    h = ad.ReLU(x @ w)
+    h2 = h if share else ad.ReLU(x @ w)
+    loss = ad.Einsum("ab->", h * h2) * scale
+    return ad.grad(loss, [w]) + [loss]
+
+
+def test_isomorphic_graphs_share_a_signature():
+    a, b = _sig(_mlp(0)), _sig(_mlp(1))
+    assert a is not None and a == b and hash(a) == hash(b)
+
+
+def test_signature_sees_scalars_shapes_sharing_and_attributes():
+    base = _sig(_mlp(0))
+    assert _sig(_mlp(0, scale=3.0)) != base          # a folded scalar is part of the program
+    assert _sig(_mlp(0, width=6)) != base            # leaf shapes
+    assert _sig(_mlp(0, share=False)) != base        # the same tree with a different sharing pattern is a different DAG
+    x = ad.Variable(np.ones((3, 4)))
+    assert _sig([ad.Einsum("ab->a", x)]) != _sig([ad.Einsum("ab->b", x)])
+    assert _sig([x[0:2]]) != _sig([x[1:3]])
+    assert _sig([ad.ReduceSumKeepDims(x, axes=[0])]) != _sig([ad.ReduceSumKeepDims(x, axes=[1])])
+    assert _sig([ad.Concat(x, x, axis=0)]) != _sig([ad.Concat(x, x, axis=1)])
+    assert _sig([ad.Reshape(x, (4, 3))]) != _sig([ad.Reshape(x, (2, 6))])
+    assert _sig([ad.Pad(x, ((1, 1), (0, 0)), 0.0)]) != _sig([ad.Pad(x, ((1, 1), (0, 0)), 1.0)])
+
+
+def test_order_and_multiplicity_of_outputs_matter():
+    x = ad.Variable(np.ones((3, 4)))
+    a, b = ad.Exp(x), ad.Log(x)
+    assert _sig([a, b]) != _sig([b, a])
+    assert _sig([a, a]) != _sig([a])
+
+
+def test_graphs_that_cannot_be_taped_are_rejected():
+    class Mine(ad.Node):                             # a user-defined numpy op (README: "easy to add your own operations")
+        def __init__(self, n):
+            super().__init__([n], "Mine")
+            self.shape = self.children[0].shape
+
+        def _eval(self):
+            return np.sin(self.children[0]())
+
+    class MyRelu(ad.ReLU):                           # a subclass of a known op may compute anything
+        pass
+
+    x = ad.Variable(np.ones((3, 4)))
+    assert _sig([Mine(x) + 1.0]) is None
+    assert _sig([MyRelu(x)]) is None
+    assert _sig([ad.ReLU(x)]) is not None
+    assert _sig([ad.checkpoint(lambda v: ad.Exp(v))(x)]) is None
+
+
+def test_lookup_records_on_second_sighting_and_replays_after_store():
+    tape.clear()
+    sig = ("unit-test", 1)
+    assert tape.lookup(sig) == (None, False)
+    assert tape.lookup(sig) == (None, True)
+    tape.store(sig, None)                            # recording failed: never try again
+    assert tape.lookup(sig) == (None, False)
+    sig2 = ("unit-test", 2)
+    tape.lookup(sig2); tape.lookup(sig2)
+    marker = object()
+    tape.store(sig2, marker)
+    assert tape.lookup(sig2) == (marker, False)
+    tape.clear()
