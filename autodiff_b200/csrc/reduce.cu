@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -840,10 +841,16 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
         const int w = threadIdx.x;
         double M = w < NW ? sm[0][w] : -INFINITY, S = w < NW ? sm[1][w] : 0.0;
         double L = w < NW ? sm[2][w] : 0.0, D = w < NW ? sm[3][w] : 0.0;
+        // rescale every warp's sum to the row max with ONE exp per lane (max first, then a plain sum): the chain the
+        // other warps wait behind is 8 shuffles + 1 exp instead of log2(NW) dependent (exp, exp) pairs
+        double Mx = M;
+#pragma unroll
+        for (int off = NW / 2; off > 0; off >>= 1) Mx = fmax(Mx, __shfl_xor_sync(0xffffffffu, Mx, off));
+        S = (M == -INFINITY) ? 0.0 : S * exp(M - Mx);
+        M = Mx;
 #pragma unroll
         for (int off = NW / 2; off > 0; off >>= 1) {
-            const double m2 = __shfl_xor_sync(0xffffffffu, M, off), s2 = __shfl_xor_sync(0xffffffffu, S, off);
-            lse_combine(M, S, m2, s2);
+            S += __shfl_xor_sync(0xffffffffu, S, off);
             L += __shfl_xor_sync(0xffffffffu, L, off);
             D += __shfl_xor_sync(0xffffffffu, D, off);
         }
@@ -855,6 +862,10 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
         }
     }
 }
+
+// (A TMA-staged persistent variant - one 512-thread CTA per SM, rows prefetched into a shared-memory ring with 1-D bulk
+// copies - was measured at 0.47 of the HBM roof against 0.66 for the kernel above: with 64 KB per row only one CTA fits
+// per SM, and the per-row dependent chain (max -> exp -> sum -> log) then has no second CTA to overlap with.)
 
 int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st) {
     if (labels->rank != 2 || logits->rank != 2) return set_error("softmax_ce: labels and logits must be 2-D (got %d, %d)", labels->rank, logits->rank);
