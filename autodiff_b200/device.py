@@ -318,12 +318,28 @@ def to_device(array):
     a = np.asarray(array)
     if a.dtype != np.float64:
         a = a.astype(np.float64)
+    if 0 < a.size <= _SMALL_CONST_ELEMS:
+        # tiny host constants (the `np.array([1])` operand of every Softmax, reference ops.py:428-432; python numbers used as
+        # einsum operands) are uploaded once per distinct content: a synchronous upload each time would drain the
+        # stream hundreds of times per evaluation of an unrolled RNN.  Device arrays are never written in place.
+        key = (a.shape, a.tobytes())
+        hit = _small_const_cache.get(key)
+        if hit is not None:
+            return hit
     out = DeviceArray.empty(a.shape)
     if a.size == 0:
         return out
     _enqueue_upload(a, out, C.c_void_p(stream_ptr()))
     synchronize()   # the source may be pageable and may be mutated/freed by the caller right after
+    if a.size <= _SMALL_CONST_ELEMS:
+        if len(_small_const_cache) >= 4096:
+            _small_const_cache.clear()
+        _small_const_cache[(a.shape, a.tobytes())] = out
     return out
+
+
+_SMALL_CONST_ELEMS = 16
+_small_const_cache = {}
 
 
 def to_device_async(array, stream):

@@ -59,7 +59,15 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True):
 
     def ready(node):                               # fires when a gradient's kernels are queued
         if dist is not None and node is not cost:
-            works.append(allreduce_async(node._dev, dist))
+            d = node._dev
+            if d.size <= 16 or any(st == 0 and dim > 1 for dim, st in zip(d.shape, d.strides)):
+                # a gradient that ALIASES a shared constant (broadcast ones, a cached tiny upload) must not be reduced
+                # in place: give it storage of its own first
+                from .device import copy_device
+                own = DeviceArray.empty(d.shape)
+                copy_device(d, own)
+                node._dev = d = own
+            works.append(allreduce_async(d, dist))
     # one fusion plan (and one launch tape) over all outputs; last layer's dW is needed first, so it is evaluated
     # first and its all-reduce overlaps the rest of the backward pass
     evaluate_many(list(reversed(grads)) + ([cost] if read_loss else []), on_ready=ready)

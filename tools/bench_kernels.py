@@ -26,6 +26,46 @@ def dev(shape, positive=False):
     return ad.to_device(a)
 
 
+def cpu_time(fn, nbytes_sample):
+    """The reference's numpy expression for the same op on a bounded host sample (1 core: ufuncs and np.einsum are
+    single-threaded): returns GB/s of algorithmic bytes."""
+    import time
+    fn()
+    t0 = time.perf_counter()
+    fn()
+    return nbytes_sample / (time.perf_counter() - t0) / 1e9
+
+
+SAMPLE = (2048, 2048)
+hx = rng.standard_normal(SAMPLE); hy = rng.random(SAMPLE) + 0.5; hb = rng.standard_normal(SAMPLE[1])
+hn = hx.size
+CPU = {   # name prefix -> (numpy restatement of the reference's _eval body, algorithmic bytes of the sample)
+    "copy": (lambda: np.concatenate((hx, np.ones((SAMPLE[0], 1))), axis=1), 16 * hn),
+    "add x+y": (lambda: np.array(sum([hx, hy])), 24 * hn),
+    "mul x*y*b": (lambda: (hx * hy) * hb, 24 * hn),
+    "relu": (lambda: hx * (hx > 0), 16 * hn),
+    "recipr": (lambda: 1 / (hy + 1e-12), 16 * hn),
+    "exp": (lambda: np.exp(hx), 16 * hn),
+    "sigmoid": (lambda: 1 / (1 + np.exp(-hx)), 16 * hn),
+    "log": (lambda: np.log(hy + 1e-12), 16 * hn),
+    "tanh macro": (lambda: (lambda v: (1 + -v) * (1 / (1 + v + 1e-12)))(np.exp(-2 * hx)), 16 * hn),
+    "relu grad": (lambda: (lambda r: hy * r * (1 / (r + 1e-12)))(hx * (hx > 0)), 24 * hn),
+    "sum rows": (lambda: np.einsum("ab->a", hx), 8 * hn),
+    "sum cols": (lambda: np.einsum("ab->b", hx), 8 * hn),
+    "sum all": (lambda: np.einsum("ab->", hx), 8 * hn),
+    "softmax denominator": (lambda: np.einsum("bi,o->bo", hx, np.array([1])), 8 * hn),
+    "frobenius": (lambda: np.sqrt(np.sum(np.square(hx))), 8 * hn),
+    "softmax_ce": (lambda: (lambda z, l: -np.sum(l * z - l * (np.max(z, -1, keepdims=True) + np.log(np.sum(np.exp(z - np.max(z, -1, keepdims=True)), -1, keepdims=True))), -1))(hx, hy), 16 * hn),
+    "adam": (lambda: (lambda m, v: hx - 1e-3 * m / (np.sqrt(v) + 1e-8))(0.9 * hx + 0.1 * hy, 0.999 * hy + 0.001 * hy * hy), 56 * hn),
+}
+h4 = rng.standard_normal((48, 48, 48, 48)); h2 = rng.standard_normal((48, 48))
+CPU["C2c fwd"] = (lambda: np.einsum("ijkl,jl->ik", h4, h2), 8 * h4.size)
+CPU["C2c dB"] = (lambda: np.einsum("ijkl,ik->jl", h4, h2), 8 * h4.size)
+CPU["C2c dA"] = (lambda: np.einsum("ik,jl->ijkl", h2, h2), 8 * h4.size)
+hg = rng.standard_normal((768, 768))
+CPU["gemm"] = (lambda: np.einsum("ij,jk->ik", hg, hg), None)
+
+
 def timeit(name, build, nbytes, flops=None, reps=8):
     """GPU time per op with `reps` ops queued back to back (graphs are built before the clock starts, so host
     graph-construction time is excluded and launch overhead overlaps with the previous kernel)."""
@@ -55,6 +95,15 @@ def timeit(name, build, nbytes, flops=None, reps=8):
            "host_ms": round(host, 4)}
     if flops:
         row["TFLOP/s"] = round(flops / (best * 1e-3) / 1e12, 2)
+    for prefix, (fn, nb) in CPU.items():
+        if name.startswith(prefix):
+            if nb is None:
+                import time
+                fn(); t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+                row["numpy_1core_TFLOP/s"] = round(2.0 * 768 ** 3 / dt / 1e12, 5)
+            else:
+                row["numpy_1core_GB/s"] = round(cpu_time(fn, nb), 2)
+            break
     results.append(row)
     print(row, flush=True)
 
