@@ -9,6 +9,7 @@ import numpy as np
 from .. import _lib
 from ..device import DeviceArray, stream_ptr, to_device, torch
 from .node import ConstFill, Node, Variable
+from .utils import gc_paused
 
 fusion_enabled = True   # set False to run one kernel per node (debugging / A-B measurements)
 kernel_timings = None   # bench.py sets this to a list; Einsum then records (description, start, stop) CUDA events
@@ -148,12 +149,18 @@ def _execute(top, plan):
         stack.pop()
 
 
+_tape_mod = None
+
+
 def evaluate_many(tops, on_ready=None):
     """Evaluates several graph outputs with one fusion plan (consumer counts span all of them).
     `on_ready(node)` fires as soon as each output's kernels are queued (used to overlap all-reduces).
     Structures seen before are replayed from a launch tape (core/tape.py) instead of being planned again."""
-    from . import tape
-    from .utils import gc_paused
+    global _tape_mod
+    if _tape_mod is None:
+        from . import tape as _t
+        _tape_mod = _t
+    tape = _tape_mod
     tops = list(tops)
     with gc_paused():
         rec, sig, scanned = None, None, None

@@ -20,6 +20,17 @@ import numpy as np
 from ..device import DeviceArray, to_device, to_host
 
 
+_ops = None        # autodiff_b200.core.ops / .reshape / .engine, bound on first use (they import this module, so not at import time)
+_reshape = None
+_engine = None
+
+
+def _mods():
+    global _ops, _reshape, _engine
+    from . import engine, ops, reshape
+    _ops, _reshape, _engine = ops, reshape, engine
+
+
 class Node:
     epsilon = 1e-12          # reference node.py:8
     id = 0
@@ -55,8 +66,9 @@ class Node:
 
     def _download(self, dev):
         host = to_host(dev)
-        from .engine import check_pending_flags
-        check_pending_flags()
+        if _engine is None:
+            _mods()
+        _engine.check_pending_flags()
         if host.ndim == 0 and not self._scalar_as_array:
             return host[()]          # numpy scalar, like the reference's ufunc results on 0-d input
         return host
@@ -77,8 +89,9 @@ class Node:
     def eval(self):
         if self._host is None:
             if self._dev is None:
-                from .engine import evaluate
-                evaluate(self)
+                if _engine is None:
+                    _mods()
+                _engine.evaluate(self)
             if self._host is None:
                 self._host = self._download(self._dev)
         return self._host
@@ -86,8 +99,9 @@ class Node:
     def eval_device(self):
         """Evaluates (memoised) and returns the device-resident value without any device->host copy."""
         if self._dev is None:
-            from .engine import evaluate
-            evaluate(self)
+            if _engine is None:
+                _mods()
+            _engine.evaluate(self)
             if self._dev is None:           # foreign node that produced a host value
                 self._dev = to_device(np.asarray(self._host))
         return self._dev
@@ -107,12 +121,14 @@ class Node:
         return self.name
 
     def __add__(self, other):
-        from .ops import Add
-        return Add(self, other)
+        if _ops is None:
+            _mods()
+        return _ops.Add(self, other)
 
     def __neg__(self):
-        from .ops import Negate
-        return Negate(self)
+        if _ops is None:
+            _mods()
+        return _ops.Negate(self)
 
     def __sub__(self, other):
         return self.__add__(other.__neg__())
@@ -121,38 +137,45 @@ class Node:
         return self.__neg__().__add__(other)
 
     def __mul__(self, other):
-        from .ops import Mul
-        return Mul(self, other)
+        if _ops is None:
+            _mods()
+        return _ops.Mul(self, other)
 
     def __matmul__(self, other):
-        from .ops import MatMul
-        return MatMul(self, other)
+        if _ops is None:
+            _mods()
+        return _ops.MatMul(self, other)
 
     def __rmatmul__(self, other):
-        from .ops import MatMul
-        return MatMul(other, self)
+        if _ops is None:
+            _mods()
+        return _ops.MatMul(other, self)
 
     def __imatmul__(self, other):
         return self.__matmul__(other)
 
     def __truediv__(self, other):
-        from .ops import Recipr
-        return self.__mul__(Recipr(other))
+        if _ops is None:
+            _mods()
+        return self.__mul__(_ops.Recipr(other))
 
     def __rtruediv__(self, other):
-        from .ops import Recipr
-        return Recipr(self).__mul__(other)
+        if _ops is None:
+            _mods()
+        return _ops.Recipr(self).__mul__(other)
 
     def __pow__(self, power, modulo=None):
-        from .ops import Pow
-        return Pow(self, power)
+        if _ops is None:
+            _mods()
+        return _ops.Pow(self, power)
 
     __rmul__ = __mul__
     __radd__ = __add__
 
     def __getitem__(self, item):
-        from .reshape import Slice
-        return Slice(self, item)
+        if _reshape is None:
+            _mods()
+        return _reshape.Slice(self, item)
 
 
 class Variable(Node):

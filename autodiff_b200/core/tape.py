@@ -290,12 +290,13 @@ def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
     n_ext = tape.n_ext
     # values first: on_ready callbacks (gradient all-reduce) use node._dev as soon as a top's kernels are queued
     slot_off = tape.slot_off
+    make = DeviceArray._make
     for i, j, off, shape, strides in tape.values:
         n = order[i]
         if j >= n_ext:
-            n._dev = DeviceArray(arena, slot_off[j - n_ext] + off, shape, strides)
+            n._dev = make(arena, slot_off[j - n_ext] + off, shape, strides)
         elif j >= 0:
-            n._dev = DeviceArray(base_tensors[j], off, shape, strides)
+            n._dev = make(base_tensors[j], off, shape, strides)
         else:
             n._dev = off                          # recorded DeviceArray (persistent constant / empty)
     check = _lib.check

@@ -94,6 +94,13 @@ class DeviceArray:
         self.strides = tuple(int(s) for s in strides)
         self._tensor = None         # cached adb_tensor (views are immutable)
 
+    @staticmethod
+    def _make(base, offset, shape, strides):
+        """Constructor for callers that already hold int tuples (tape replay, internal views): skips the conversions."""
+        d = object.__new__(DeviceArray)
+        d.base, d.offset, d.shape, d.strides, d._tensor = base, offset, shape, strides, None
+        return d
+
     # ---- construction
     @staticmethod
     def empty(shape):
