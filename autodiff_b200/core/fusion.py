@@ -26,11 +26,11 @@ def broadcast_shapes(*shapes):
     first = shapes[0]
     same = True
     for sh in shapes:
-        if sh is not first and tuple(sh) != tuple(first):
+        if sh is not first and sh != first:          # (a list never equals a tuple: those take the general path below)
             same = False
             break
     if same:
-        return tuple(first)
+        return first if type(first) is tuple else tuple(first)
     rank = max(len(sh) for sh in shapes)
     out = [1] * rank
     for sh in shapes:

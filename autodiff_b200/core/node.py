@@ -184,19 +184,24 @@ class Variable(Node):
     _scalar_as_array = True
 
     def __init__(self, value, name=None):
-        self._lazy_name = None
-        if name is None:
-            if isinstance(value, DeviceArray) or getattr(value, "size", 1) > 64:
-                name = None
-                self._lazy_name = value       # str(value) of a big array is slow (reference node.py:114 notes it)
-            else:
-                name = str(value)
-        super().__init__([], name)
-        if isinstance(value, numbers.Number):
+        # The name defaults to str(value) (reference node.py:113-114); it is computed on demand - str() of an array is
+        # slow and a second-order char-rnn graph creates thousands of leaves.  Node.__init__ is inlined (no children).
+        self._lazy_name = value if name is None else None
+        self._name = name
+        self.children = []
+        self._host = None
+        self._dev = None
+        self._dev_override = False
+        self.context_list = Node.context_list.copy()
+        self.id = Node.id
+        Node.id += 1
+        tv = type(value)
+        if tv is float or tv is int or (tv is not np.ndarray and tv is not DeviceArray and isinstance(value, numbers.Number)):
             self._value = np.array(value, dtype=np.float64)
+            self.shape = ()
         else:
             self._value = value
-        self.shape = tuple(self._value.shape)
+            self.shape = tuple(value.shape)
 
     @property
     def name(self):
