@@ -260,6 +260,40 @@ def run_gpu(args):
         except Exception as ex:
             extra = {"error": repr(ex)[:300]}
 
+    # ---- the TF32 variant of the contraction path (north_star: 1e-4 bar): C2a forward + both grads as 3xTF32 on tcgen05
+    tf32 = None
+    if rank == 0 and world == 1 and not args.skip_mlp:
+        try:
+            a = ad.Variable(dev_inputs["C2a"][0], name="A"); b = ad.Variable(dev_inputs["C2a"][1], name="B")
+            ref = ad.Einsum("ij,jk->ik", a, b).eval_device()
+
+            def tf_step():
+                with ad.precision("tf32x3"):
+                    x = ad.Variable(dev_inputs["C2a"][0], name="A"); y = ad.Variable(dev_inputs["C2a"][1], name="B")
+                    e = ad.Einsum("ij,jk->ik", x, y)
+                    outs = [e] + ad.grad(e, [x, y])
+                    return [o.eval_device() for o in outs]
+            for _ in range(2):
+                got = tf_step()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(3):
+                got = tf_step()
+            t1.record()
+            torch.cuda.synchronize()
+            h_ref = ad.to_host(ref)[:64]
+            h_got = ad.to_host(got[0])[:64]
+            rel = float(np.max(np.abs(h_got - h_ref)) / np.max(np.abs(h_ref)))
+            tf_ms = t0.elapsed_time(t1) / 3
+            tf32 = {"tflops_effective": round(3 * einsum_flops(*cfg["C2a"]) / (tf_ms * 1e-3) / 1e12, 2), "ms_per_step": round(tf_ms, 3),
+                    "rel_err_vs_fp64": rel, "bar": 1e-4,
+                    "what": "C2a 'ij,jk->ik' 8192^2 forward + both grads with ad.precision('tf32x3'): fp64 operands split into hi+lo tf32, "
+                            "three tcgen05.mma (kind::tf32) products per tile accumulated in TMEM, fp64 in / fp64 out; includes the split passes"}
+            del got, ref
+        except Exception as ex:
+            tf32 = {"error": repr(ex)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = run_reference_sample(reps=1, courtesy=True)
@@ -273,7 +307,7 @@ def run_gpu(args):
                            "flop_per_step": flops, "l2": "inputs (512 MiB - 2 GiB each) exceed the 126 MB L2",
                            "parallelism": "replicas x%d (the sweep has no exchange step)" % world},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches) * world,
-                "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "mlp_train": mlp, "other_configs": extra}
+                "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "mlp_train": mlp, "other_configs": extra, "tf32x3_variant": tf32}
         print(json.dumps(line))
         if os.environ.get("ADB_EW_STATS"):        # which elementwise programs ran (input of tools/gen_ewise_catalog.py)
             open(os.environ["ADB_EW_STATS"], "w").write(ad.ewise_stats())

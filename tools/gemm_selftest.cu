@@ -220,6 +220,17 @@ int main(int argc, char** argv) {
         fails += run_case(Case{400, 32, 50000, 1, a, b, 0, 5}, false, 0);            // skinny + split-K
     }
     printf("correctness: %d failing cases\n", fails);
+    if (argc > 1 && !strcmp(argv[1], "rnn")) {            // char-rnn (C5) shapes under every tile configuration
+        long long shp[][3] = {{512, 1024, 1024}, {512, 71, 1024}, {512, 1024, 71}, {1024, 1024, 512}, {71, 1024, 512}, {1024, 71, 512}};
+        for (auto& s : shp) {
+            const int a_kc = s[2] == 512 ? 0 : 1;        // weight gradients contract over the batch: A is MN-contiguous
+            for (int path : {0, 3, 4, 5}) {
+                if (path == 5 && s[1] > 71) continue;
+                run_case(Case{s[0], s[1], s[2], 1, a_kc, 0, 0, path}, true, 5);
+            }
+        }
+        return fails ? 1 : 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "skinny")) {
         run_case(Case{802816, 32, 400, 1, 1, 0, 0, 4}, true, 3);   // conv2 fwd, 128x128 tiles
         run_case(Case{802816, 32, 400, 1, 1, 0, 0, 5}, true, 3);   // conv2 fwd, 256x32 tiles
