@@ -22,35 +22,45 @@ IN, IMM, TMP = _lib.SRC_IN, _lib.SRC_IMM, _lib.SRC_TMP
 
 
 class Module:
-    def forward(self, *args, **kwargs):
-        with add_context(type(self).__name__):
-            return self._forward(*args, **kwargs)
-
-    def _forward(self, *args, **kwargs):
-        raise NotImplementedError()
+    """Callable graph builder: `module(...)` runs `_forward` inside a name scope carrying the class name
+    (reference high_level_ops.py:6-15; `forward` is the same entry point)."""
 
     def __call__(self, *args, **kwargs):
-        return self.forward(*args, **kwargs)
+        scope = add_context(type(self).__name__)
+        scope.__enter__()
+        try:
+            return self._forward(*args, **kwargs)
+        finally:
+            scope.__exit__(None, None, None)
+
+    forward = __call__
+
+    def _forward(self, *args, **kwargs):
+        raise NotImplementedError("%s does not define _forward" % type(self).__name__)
+
+
+_NN_SIZES_ERROR = ("Sizes represent the layer sizes and needs to have at least two values for one weight"
+                   " matrix to exist!")
 
 
 class NN(Module):
+    """MLP of reference high_level_ops.py:18-38: layer i owns ONE (in_i + 1, out_i) matrix drawn as randn * 0.01 whose
+    last row is the bias - the input gets a column of ones concatenated before every matmul - and every layer but the
+    last is followed by ReLU.  The ones column is a `ConstFill` (never materialised) instead of np.ones((batch, 1))."""
+
     def __init__(self, sizes):
         if len(sizes) < 2:
-            raise ValueError("Sizes represent the layer sizes and needs to have at least two values for one weight"
-                             " matrix to exist!")
+            raise ValueError(_NN_SIZES_ERROR)
         self.sizes = sizes
-        self.w = []
-        for i, (inp, out) in enumerate(zip(self.sizes, self.sizes[1:])):
-            w_initial = np.random.randn(inp + 1, out) * 0.01
-            self.w.append(Variable(w_initial, name="w" + str(i)))
+        fan = list(zip(sizes[:-1], sizes[1:]))
+        self.w = [Variable(np.random.randn(n_in + 1, n_out) * 0.01, name="w%d" % k) for k, (n_in, n_out) in enumerate(fan)]
 
     def _forward(self, x):
-        first_dim = x.shape[0]
-        bias = ConstFill((first_dim, 1), 1.0, name="bias")     # reference: Variable(np.ones((first_dim, 1)))
-        for i, w in enumerate(self.w):
-            x = Concat(x, bias, axis=1)
-            x = x @ w
-            if i < len(self.w) - 1:
+        ones_col = ConstFill((x.shape[0], 1), 1.0, name="bias")
+        last = len(self.w) - 1
+        for k, weights in enumerate(self.w):
+            x = Concat(x, ones_col, axis=1) @ weights
+            if k != last:
                 x = ReLU(x)
         return x
 
@@ -70,13 +80,43 @@ def _give_back(d, kind):
 
 
 class Optimizer(Module):
+    """Call convention of reference high_level_ops.py:41-131: `new_params = opt(param_values, grad_values)` followed by
+    `opt.apply_new_weights(variables, new_params)`.  Stateful optimizers keep one entry per parameter in the lists named
+    by `STATE`; `fn` takes (leading args..., state..., param, grad) and returns (new_param, new_state...).  As in the
+    reference the stateful ones write the new values into the list they were given and return that same list."""
+    STATE = ()
+
     @staticmethod
     def apply_new_weights(weight_list, new_weight_values):
-        for w, new_w_value in zip(weight_list, new_weight_values):
-            w.value = new_w_value
+        for variable, fresh in zip(weight_list, new_weight_values):
+            variable.value = fresh
 
-    def _forward(self, *args, **kwargs):
-        raise NotImplementedError()
+    def _reset_state(self, num_params):
+        for name in self.STATE:
+            setattr(self, name, [0] * num_params)
+
+    def _leading(self):
+        return ()
+
+    def _stepped(self):
+        pass
+
+    def _forward(self, params_list, grads_list):
+        if not isinstance(params_list, list):
+            params_list = list(params_list)
+        slots = [getattr(self, name) for name in self.STATE]
+        for k in range(min(len(params_list), len(grads_list))):
+            out = self.fn(*self._leading(), *[slot[k] for slot in slots], params_list[k], grads_list[k])
+            params_list[k] = out[0]
+            for slot, value in zip(slots, out[1:]):
+                slot[k] = value
+        self._stepped()
+        return params_list
+
+
+def _moment(prev, like):
+    """Optimizer state starts as the python number 0 (reference) and lives in HBM from the first update on."""
+    return prev if isinstance(prev, DeviceArray) else DeviceArray.full(like.shape, float(prev))
 
 
 class SGDOptimizer(Optimizer):
@@ -84,7 +124,7 @@ class SGDOptimizer(Optimizer):
         self.lr = lr
 
     def _forward(self, params_list, grads_list):
-        return [self.fn(param, grad) for param, grad in zip(params_list, grads_list)]
+        return [self.fn(p, g) for p, g in zip(params_list, grads_list)]          # (a new list, as in the reference)
 
     def fn(self, param, grad):
         # param - lr * grad
@@ -97,22 +137,17 @@ class SGDOptimizer(Optimizer):
 
 class Momentum(Optimizer):
     """Accumulates gradient change through time steps (reference high_level_ops.py:64-82)."""
+    STATE = ("v",)
 
     def __init__(self, num_params, lr=0.001, gamma=0.8):
-        self.lr = lr
-        self.gamma = gamma
-        self.v = [0 for _ in range(num_params)]
-
-    def _forward(self, params_list, grads_list):
-        for i, (param, grad) in enumerate(zip(params_list, grads_list)):
-            params_list[i], self.v[i] = self.fn(self.v[i], param, grad)
-        return params_list
+        self.lr, self.gamma = lr, gamma
+        self._reset_state(num_params)
 
     def fn(self, prev_m, param, grad):
         # new_m = gamma * prev_m + grad ; param - lr * new_m
         p, kind = _as_device(param)
         g, _ = _as_device(grad)
-        m = prev_m if isinstance(prev_m, DeviceArray) else DeviceArray.full(g.shape, float(prev_m))
+        m = _moment(prev_m, g)
         code = [(_lib.EW_LOAD | IN, 2, 0.0), (_lib.EW_MUL | IMM, 0, float(self.gamma)), (_lib.EW_ADD | IN, 1, 0.0),
                 (_lib.EW_STORE_OUT, 1, 0.0),
                 (_lib.EW_MUL | IMM, 0, float(self.lr)), (_lib.EW_NEG, 0, 0.0), (_lib.EW_ADD | IN, 0, 0.0), (_lib.EW_STORE_OUT, 0, 0.0)]
@@ -122,21 +157,17 @@ class Momentum(Optimizer):
 
 class Adagrad(Optimizer):
     """Per-parameter learning rates from the running sum of squared gradients (reference high_level_ops.py:85-105)."""
+    STATE = ("run_avg",)
 
     def __init__(self, num_params, lr=0.01):
         self.lr = lr
-        self.run_avg = [0 for _ in range(num_params)]
-
-    def _forward(self, params_list, grads_list):
-        for i, (param, grad) in enumerate(zip(params_list, grads_list)):
-            params_list[i], self.run_avg[i] = self.fn(self.run_avg[i], param, grad)
-        return params_list
+        self._reset_state(num_params)
 
     def fn(self, prev_avg, param, grad):
         # new_avg = prev_avg + grad**2 ; param - lr / sqrt(new_avg + 1e-8) * grad
         p, kind = _as_device(param)
         g, _ = _as_device(grad)
-        a = prev_avg if isinstance(prev_avg, DeviceArray) else DeviceArray.full(g.shape, float(prev_avg))
+        a = _moment(prev_avg, g)
         code = [(_lib.EW_LOAD | IN, 1, 0.0), (_lib.EW_SQUARE, 0, 0.0), (_lib.EW_STORE_T, 0, 0.0),
                 (_lib.EW_LOAD | IN, 2, 0.0), (_lib.EW_ADD | TMP, 0, 0.0), (_lib.EW_STORE_OUT, 1, 0.0),
                 (_lib.EW_ADD | IMM, 0, 1e-8), (_lib.EW_SQRT, 0, 0.0), (_lib.EW_STORE_T, 0, 0.0),
@@ -147,31 +178,28 @@ class Adagrad(Optimizer):
 
 
 class Adam(Optimizer):
+    """Reference high_level_ops.py:108-131, quirk included: `step` starts at 0, so the first update is a no-op."""
     eps = 1e-8
+    STATE = ("m", "v")
 
     def __init__(self, num_params, lr=0.001, b1=0.9, b2=0.999):
-        self.lr = lr
-        self.b1 = b1
-        self.b2 = b2
+        self.lr, self.b1, self.b2 = lr, b1, b2
         self.num_params = num_params
-        self.m = [0 for _ in range(num_params)]
-        self.v = [0 for _ in range(num_params)]
         self.step = 0
+        self._reset_state(num_params)
 
-    def _forward(self, params_list, grads_list):
-        params_list = list(params_list)
-        for i, (param, grad) in enumerate(zip(params_list, grads_list)):
-            params_list[i], self.m[i], self.v[i] = self.fn(self.step, self.m[i], self.v[i], param, grad)
+    def _leading(self):
+        return (self.step,)
+
+    def _stepped(self):
         self.step += 1
-        return params_list
 
     def fn(self, step, prev_m, prev_v, param, grad):
         # new_m = b1*prev_m + (1-b1)*grad ; new_v = b2*prev_v + (1-b2)*grad**2
         # a = lr*sqrt(1-b2**step)/(1-b1**step+eps) ; param - a*new_m/(sqrt(new_v)+eps)     (high_level_ops.py:126-131)
         p, kind = _as_device(param)
         g, _ = _as_device(grad)
-        m = prev_m if isinstance(prev_m, DeviceArray) else DeviceArray.full(g.shape, float(prev_m))
-        v = prev_v if isinstance(prev_v, DeviceArray) else DeviceArray.full(g.shape, float(prev_v))
+        m, v = _moment(prev_m, g), _moment(prev_v, g)
         a = self.lr * math.sqrt(1 - self.b2 ** step) / (1 - self.b1 ** step + Adam.eps)
         code = [
             (_lib.EW_LOAD | IN, 1, 0.0), (_lib.EW_MUL | IMM, 0, float(1 - self.b1)), (_lib.EW_STORE_T, 0, 0.0),
@@ -189,14 +217,9 @@ class Adam(Optimizer):
 
 
 class NesterovMomentum(Optimizer):
-    """Unfinished in the reference too (no `fn`, high_level_ops.py:134-150): calling it raises AttributeError."""
+    """Unfinished in the reference too (it defines no `fn`, high_level_ops.py:134-150): calling it raises AttributeError."""
+    STATE = ("v",)
 
     def __init__(self, num_params, lr=0.001, gamma=0.8):
-        self.lr = lr
-        self.gamma = gamma
-        self.v = [0 for _ in range(num_params)]
-
-    def _forward(self, params_list, grads_list):
-        for i, (param, grad) in enumerate(zip(params_list, grads_list)):
-            params_list[i], self.v[i] = self.fn(self.v[i], param, grad)
-        return params_list
+        self.lr, self.gamma = lr, gamma
+        self._reset_state(num_params)

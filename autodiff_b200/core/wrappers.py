@@ -1,19 +1,35 @@
+"""`checkpoint(fn)` - gradient rematerialisation (API of reference autodiff/core/wrappers.py:5-15)."""
 from .grad import grad
 from .node import Node
 
 
-def checkpoint(fn):
-    """Gradient rematerialisation wrapper, reference autodiff/core/wrappers.py:5-15: the wrapped sub-graph is an
-    opaque node whose forward builds + evaluates a throw-away inner graph (on the device) and whose gradient
-    rebuilds it.  Superset behaviour: `shape` is inferred from fn's graph so default-seed grad() works."""
-    def wrap_in_primitive(*fn_args):
-        op = Node(children=fn_args, name=fn.__name__)
-        op._eval = lambda: fn(*fn_args)()
-        op._partial_derivative = lambda wrt, previous_grad: grad(fn(*fn_args), [wrt], previous_grad=previous_grad)[0]
-        try:
-            op.shape = fn(*fn_args).shape
-        except Exception:
-            op.shape = None
-        return op
+class _Checkpointed(Node):
+    """The sub-graph `fn(*args)` as ONE opaque node of the outer graph: nothing of it is kept between the forward value and
+    the backward pass - both rebuild the inner graph from `fn` (the reference does the same with two lambdas on a bare
+    Node).  Beyond the reference: the value stays on the device, and `shape` is inferred from the inner graph so that a
+    default-seed `grad()` through the node works."""
 
-    return wrap_in_primitive
+    def __init__(self, fn, args):
+        super().__init__(list(args), name=fn.__name__)
+        self._fn = fn
+        try:
+            self.shape = self._inner().shape
+        except Exception:
+            self.shape = None
+
+    def _inner(self):
+        return self._fn(*self.children)
+
+    def _eval_device(self):
+        return self._inner().eval_device()
+
+    def _partial_derivative(self, wrt, previous_grad):
+        return grad(self._inner(), [wrt], previous_grad=previous_grad)[0]
+
+
+def checkpoint(fn):
+    def build(*fn_args):
+        return _Checkpointed(fn, fn_args)
+
+    build.__name__ = getattr(fn, "__name__", "checkpoint")
+    return build
