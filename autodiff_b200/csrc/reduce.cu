@@ -740,44 +740,11 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const double* __restric
 }
 
 // Wide rows: one CTA per row, the row of logits AND labels held in registers (K quads per thread each), so HBM is
-// read exactly once; three block reductions (max, [sum exp, sum labels], dot).  cols <= 256 * 4 * K.
-template <int NW>
-__device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    __syncthreads();                       // previous use of sm is over
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) t += sm[w];
-    return t;
-}
-template <int NW>
-__device__ __forceinline__ double block_reduce_max(double v, double* sm) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = sm[0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) t = fmax(t, sm[w]);
-    return t;
-}
-
-// K quads per thread, NT threads per CTA: cols <= NT * 4 * K.  Single pass ("online" log-sum-exp): every thread
-// reduces its own elements to (max m, sum exp(z - m), sum l, sum l*z); pairs (m, s) combine as
-// (M, s1*exp(m1-M) + s2*exp(m2-M)) with M = max(m1, m2) through warp shuffles and ONE shared-memory exchange, so a
-// row costs one block barrier instead of four dependent phases.  out = -(sum l*z - lse * sum l), the reference's
+// read exactly once.  K quads per thread, NT threads per CTA: cols <= NT * 4 * K.  Single pass ("online" log-sum-exp): every warp reduces
+// its elements to (max m_w, sum exp(z - m_w), sum l, sum l*z) - the warp max first, so each element costs one exp -
+// and after ONE shared-memory exchange warp 0 rescales the per-warp sums to the row max (one exp per warp) and adds
+// them: a row costs one block barrier instead of four dependent phases.  out = -(sum l*z - lse * sum l), the reference's
 // -sum(l*z - l*lse) re-associated (error ~1e-16 of the terms; parity bar 1e-12).
-__device__ __forceinline__ void lse_combine(double& m, double& s, double m2, double s2) {
-    const double M = fmax(m, m2);
-    if (M == -INFINITY) { s = s + s2; m = M; return; }     // both empty so far (or all -inf: numpy gives nan, see below)
-    s = s * exp(m - M) + s2 * exp(m2 - M);
-    m = M;
-}
-
 template <int K, int NT>
 __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
                                                              long long z_sr, double* __restrict__ out, long long o_s, long long rows,
