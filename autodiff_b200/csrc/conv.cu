@@ -37,6 +37,37 @@ __global__ void __launch_bounds__(256) col2im_kernel(const double* __restrict__ 
     }
 }
 
+// Channel-quad variant (C % 4 == 0, 32-byte aligned rows): one thread gathers 4 consecutive channels of one pixel with
+// 256-bit loads; the lanes of a warp cover consecutive (pixel, channel-quad) pairs, i.e. whole 128-byte channel runs.
+__global__ void __launch_bounds__(256) col2im_quad_kernel(const double* __restrict__ cols, double* __restrict__ dx, int N, int H, int W, int CQ,
+                                                          int kh, int kw, long long x_sn, long long x_sh, long long x_sw,
+                                                          long long cols_row_stride) {
+    const int OH = H - kh + 1, OW = W - kw + 1;
+    const long long total = (long long)N * H * W * CQ;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cq = (int)(i % CQ);
+    long long r = i / CQ;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    const int C = CQ * 4;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int a_lo = y - (OH - 1) > 0 ? y - (OH - 1) : 0, a_hi = y < kh - 1 ? y : kh - 1;
+    const int b_lo = x - (OW - 1) > 0 ? x - (OW - 1) : 0, b_hi = x < kw - 1 ? x : kw - 1;
+    for (int a = a_lo; a <= a_hi; ++a) {
+        const long long rowbase = ((long long)n * OH + (y - a)) * OW;
+        for (int b = b_lo; b <= b_hi; ++b) {
+            const double* p = cols + (rowbase + (x - b)) * cols_row_stride + ((long long)a * kw + b) * C + cq * 4;
+            double v0, v1, v2, v3;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3) : "l"(p));
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+    }
+    double* q = dx + n * x_sn + y * x_sh + x * x_sw + cq * 4;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(q), "d"(a0), "d"(a1), "d"(a2), "d"(a3) : "memory");
+}
+
 }  // namespace adb
 
 extern "C" {
@@ -69,6 +100,18 @@ int adb_col2im(const adb_tensor* cols, int kh, int kw, const adb_tensor* dx, voi
     if (cols->stride[1] != 1) return adb::set_error("col2im: cols must have unit column stride");
     if (N * H * W * C == 0) return 0;
     if (H > 0x7fffffff / 4 || W > 0x7fffffff / 4) return adb::set_error("col2im: image too large");
+    const bool quad = C % 4 == 0 && dx->stride[3] == 1 && cols->stride[0] % 4 == 0 && dx->stride[0] % 4 == 0 && dx->stride[1] % 4 == 0 &&
+                      dx->stride[2] % 4 == 0 && ((reinterpret_cast<uintptr_t>(cols->ptr) | reinterpret_cast<uintptr_t>(dx->ptr)) & 31) == 0 &&
+                      N * H * W * (C / 4) < (1LL << 31) * 256;
+    if (quad) {
+        const long long threads = N * H * W * (C / 4);
+        adb::col2im_quad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            cols->ptr, dx->ptr, (int)N, (int)H, (int)W, (int)(C / 4), kh, kw, dx->stride[0], dx->stride[1], dx->stride[2], cols->stride[0]);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return adb::set_error("col2im launch failed: %s", cudaGetErrorString(e));
+        adb::count_launch();
+        return 0;
+    }
     long long blocks = (N * H * W * C + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     adb::col2im_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

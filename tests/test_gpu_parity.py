@@ -329,6 +329,18 @@ def test_conv_im2col_forward_and_grads(ad):
     lhs = float(np.sum(np.asarray(ad.Im2Col(ad.Variable(x, name="x"), 3, 2)()) * c))
     rhs = float(np.sum(x * np.asarray(ad.Col2Im(ad.Variable(c, name="c"), x.shape, 3, 2)())))
     assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
+    # channel counts that are multiples of 4 take the 256-bit col2im kernel
+    for C_, kh, kw in ((8, 3, 3), (16, 5, 5), (4, 1, 2)):
+        xi = rng.standard_normal((2, 11, 9, C_))
+        oh, ow = 11 - kh + 1, 9 - kw + 1
+        c = rng.standard_normal((2 * oh * ow, kh * kw * C_))
+        got = np.asarray(ad.Col2Im(ad.Variable(c, name="c"), xi.shape, kh, kw)())
+        ref = np.zeros_like(xi)
+        c6 = c.reshape(2, oh, ow, kh, kw, C_)
+        for a in range(kh):
+            for b in range(kw):
+                ref[:, a:a + oh, b:b + ow, :] += c6[:, :, :, a, b, :]
+        check(got, ref, tol=1e-13, what="col2im quad C=%d" % C_)
 
 
 def test_evaluate_many_and_fusion_toggle(ad):
