@@ -489,7 +489,10 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             tile_pref = !e ? 0 : (!strcmp(e, "small") ? 1 : (!strcmp(e, "big") ? 2 : 0));
         }
         const bool skinny = force_path == 5 || (force_path == 0 && tile_pref == 0 && N <= 32 && M >= 256);
-        const bool small = !skinny && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && waste_big > 1.05))));
+        // short K (<= 8 k-tiles): a CTA is mostly prologue + epilogue, so two 64x64 CTAs per SM that overlap each other beat
+        // one 128x128 CTA (conv dX 802816x400x32: 1.38 -> 1.05 ms)
+        const bool short_k = (K + BK - 1) / BK <= 8;
+        const bool small = !skinny && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && (waste_big > 1.05 || short_k)))));
         const int bm = skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM, bn = skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
         const long long slots = small ? 296 : 148;

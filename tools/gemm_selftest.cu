@@ -231,6 +231,12 @@ int main(int argc, char** argv) {
         }
         return fails ? 1 : 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "shortk")) {          // conv dX: huge M, short K (write-dominated)
+        for (int path : {0, 3, 4}) run_case(Case{802816, 400, 32, 1, 1, 1, 0, path}, true, 3);
+        for (int path : {0, 3, 4}) run_case(Case{802816, 400, 32, 1, 1, 0, 0, path}, true, 3);
+        for (int path : {0, 3, 4}) run_case(Case{65536, 1024, 64, 1, 1, 1, 0, path}, true, 3);
+        return fails ? 1 : 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "skinny")) {
         run_case(Case{802816, 32, 400, 1, 1, 0, 0, 4}, true, 3);   // conv2 fwd, 128x128 tiles
         run_case(Case{802816, 32, 400, 1, 1, 0, 0, 5}, true, 3);   // conv2 fwd, 256x32 tiles
