@@ -8,13 +8,18 @@
 // which gives ~1e-7 relative error.
 //
 //   split_tf32_kernel : fp64 (any strides) -> two K-major fp32 matrices (hi, lo) per operand, zero-padded pitch
-//   gemm_tf32x3_kernel: TMA (128B swizzle) -> 3-stage smem ring -> tcgen05.mma.kind::tf32 (M=128, N=128, K=8)
-//                       issued by one thread, accumulator in 128 TMEM columns -> tcgen05.ld -> fp64 -> C
+//   gemm_tf32x3_kernel<MT>: TMA (128B swizzle) -> smem ring -> tcgen05.mma.kind::tf32 (M=128, N=128, K=8) issued by one
+//                       thread, MT accumulators of 128 TMEM columns each -> tcgen05.ld -> fp64 -> C.  MT = 2 stacks two
+//                       128-row tiles on the same B tiles (256x128 per CTA, 2 stages of 96 KiB); measured 8192^3:
+//                       6.15 ms vs 6.40 ms for MT = 1 (3 stages of 64 KiB), i.e. ~215 TFLOP/s effective = 645 TFLOP/s of
+//                       raw tf32 MMA inside the GEMM kernel, ~0.78 of what the cuBLAS bf16 burst figure of this pool
+//                       (1683 of 2250 nominal) suggests a tf32 kernel can sustain
 //   warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (one TMEM lane quadrant each)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "adb_internal.h"
@@ -23,13 +28,18 @@ namespace adb {
 
 namespace tf32 {
 
-constexpr int BM = 128, BN = 128, BK = 32;       // BK * 4 B = 128 B = one swizzle row
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;          // 16 KiB (A_hi, A_lo, B_hi, B_lo are each one such tile)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // 64 KiB
+constexpr int BM = 128, BN = 128, BK = 32;       // one tcgen05.mma: M = 128, N = 128; BK * 4 B = 128 B = one swizzle row
+constexpr int TILE_BYTES = BM * BK * 4;          // 16 KiB: 128 rows of one operand matrix for one k-block
 constexpr int THREADS = 256;
-constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 64;
-constexpr int TMEM_COLS = 128;
+// MT = number of 128-row MMA tiles a CTA stacks along M.  The kernel is L2-bandwidth-bound (4 operand tiles per 3 MMAs):
+// with MT = 2 the B tiles of a stage feed two accumulators, 96 KiB per 256x128x32 instead of 64 KiB per 128x128x32.
+template <int MT>
+struct Cfg {
+    static constexpr int STAGES = MT == 1 ? 3 : 2;
+    static constexpr int STAGE_BYTES = (2 * MT + 2) * TILE_BYTES;     // A_hi, A_lo (MT tiles each), B_hi, B_lo
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 64;
+    static constexpr int TMEM_COLS = 128 * MT;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -100,9 +110,12 @@ struct Params {
     long long c_sm, c_sn, c_sb, c_ss;
 };
 
+template <int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const Params p) {
+    constexpr int STAGES = Cfg<MT>::STAGES, STAGE_BYTES = Cfg<MT>::STAGE_BYTES, TMEM_COLS = Cfg<MT>::TMEM_COLS;
+    constexpr int A_BYTES = MT * TILE_BYTES;          // one A matrix (hi or lo) of a stage
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -115,7 +128,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-    const int m0 = tm * BM, n0 = tn * BN;
+    const int m0 = tm * BM * MT, n0 = tn * BN;
     const int batch = blockIdx.y;
     const int total_kb = (p.K + BK - 1) / BK;
     const int kb_first = blockIdx.z * p.kb_per_split;
@@ -150,10 +163,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 mbar_expect_tx(fb, STAGE_BYTES);
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
                 const int k0 = (kb_first + kb) * BK;
-                tma_load_3d(st, &tmAh, fb, k0, m0, batch);
-                tma_load_3d(st + TILE_BYTES, &tmAl, fb, k0, m0, batch);
-                tma_load_3d(st + 2 * TILE_BYTES, &tmBh, fb, k0, n0, batch);
-                tma_load_3d(st + 3 * TILE_BYTES, &tmBl, fb, k0, n0, batch);
+                tma_load_3d(st, &tmAh, fb, k0, m0, batch);                       // box = (BK, 128 * MT rows)
+                tma_load_3d(st + A_BYTES, &tmAl, fb, k0, m0, batch);
+                tma_load_3d(st + 2 * A_BYTES, &tmBh, fb, k0, n0, batch);
+                tma_load_3d(st + 2 * A_BYTES + TILE_BYTES, &tmBl, fb, k0, n0, batch);
             }
         }
     } else if (warp == 1) {
@@ -166,14 +179,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t dAh = make_desc(st), dAl = make_desc(st + TILE_BYTES);
-                const uint64_t dBh = make_desc(st + 2 * TILE_BYTES), dBl = make_desc(st + 3 * TILE_BYTES);
+                const uint64_t dBh = make_desc(st + 2 * A_BYTES), dBl = make_desc(st + 2 * A_BYTES + TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K = 8 step inside the swizzled row
-                    umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
-                    umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
-                    umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, 1u);
+                for (int mt = 0; mt < MT; ++mt) {           // accumulator mt = TMEM columns [128 * mt, +128), A rows [128 * mt, +128)
+                    const uint64_t dAh = make_desc(st + mt * TILE_BYTES), dAl = make_desc(st + A_BYTES + mt * TILE_BYTES);
+                    const uint32_t acc = tmem_base + (uint32_t)(mt * BN);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K = 8 step inside the swizzled row
+                        umma_tf32(acc, dAl + adv, dBh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
+                        umma_tf32(acc, dAh + adv, dBl + adv, idesc, 1u);
+                        umma_tf32(acc, dAh + adv, dBh + adv, idesc, 1u);
+                    }
                 }
                 umma_commit(empty0 + 8 * s);           // frees the smem slot once these MMAs have read it
             }
@@ -184,12 +201,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int quad = warp & 3;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + quad * 32 + lane;
-        double* crow = p.C + (long long)blockIdx.z * p.c_ss + (long long)batch * p.c_sb + (long long)row * p.c_sm;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int mc = 0; mc < MT * (BN / 32); ++mc) {
+            const int mt = mc / (BN / 32), c = mc % (BN / 32);
+            const int row = m0 + mt * BM + quad * 32 + lane;
+            double* crow = p.C + (long long)blockIdx.z * p.c_ss + (long long)batch * p.c_sb + (long long)row * p.c_sm;
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c * 32);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -259,10 +277,10 @@ static bool load_encode() {
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     return true;
 }
-static bool make_tmap_f32(CUtensorMap* map, const float* base, long long K, long long rows, long long batch, long long Kp) {
+static bool make_tmap_f32(CUtensorMap* map, const float* base, long long K, long long rows, long long batch, long long Kp, int box_rows) {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)Kp * 4ull, (cuuint64_t)Kp * (cuuint64_t)rows * 4ull};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -287,15 +305,21 @@ int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
     split_tf32_kernel<<<grid_for(a_elems), 256, 0, st>>>(d->A, d->a_sm, d->a_sk, d->a_sb, a_hi, a_lo, M, K, Kp, batch);
     split_tf32_kernel<<<grid_for(b_elems), 256, 0, st>>>(d->B, d->b_sn, d->b_sk, d->b_sb, b_hi, b_lo, N, K, Kp, batch);
     count_launch(2);
+    // 256-row CTA tiles (two accumulators sharing the B tiles) when there are enough of them to fill the GPU; ADB_TF32_MT=1|2 overrides
+    static int mt_pref = -1;
+    if (mt_pref < 0) { const char* ev = getenv("ADB_TF32_MT"); mt_pref = ev ? atoi(ev) : 0; }
+    const long long tiles256 = ((M + 255) / 256) * ((N + BN - 1) / BN) * batch;
+    const int MT = mt_pref == 1 ? 1 : (mt_pref == 2 ? 2 : (tiles256 >= 148 ? 2 : 1));
     CUtensorMap tAh, tAl, tBh, tBl;
-    if (!make_tmap_f32(&tAh, a_hi, K, M, batch, Kp) || !make_tmap_f32(&tAl, a_lo, K, M, batch, Kp) ||
-        !make_tmap_f32(&tBh, b_hi, K, N, batch, Kp) || !make_tmap_f32(&tBl, b_lo, K, N, batch, Kp)) {
+    if (!make_tmap_f32(&tAh, a_hi, K, M, batch, Kp, BM * MT) || !make_tmap_f32(&tAl, a_lo, K, M, batch, Kp, BM * MT) ||
+        !make_tmap_f32(&tBh, b_hi, K, N, batch, Kp, BN) || !make_tmap_f32(&tBl, b_lo, K, N, batch, Kp, BN)) {
         cudaFreeAsync(ws, st);
         return set_error("gemm_tf32x3: cuTensorMapEncodeTiled rejected the operands");
     }
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        e = cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM);
         if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm_tf32x3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
         attr_set = true;
     }
@@ -315,12 +339,13 @@ int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
     }
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
+    p.tiles_m = (int)((M + BM * MT - 1) / (BM * MT)); p.tiles_n = (int)((N + BN - 1) / BN);
     p.kb_per_split = kb_per_split; p._pad = 0;
     if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
     else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
     dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
-    gemm_tf32x3_kernel<<<grid, THREADS, SMEM, st>>>(tAh, tAl, tBh, tBl, p);
+    if (MT == 2) gemm_tf32x3_kernel<2><<<grid, THREADS, Cfg<2>::SMEM, st>>>(tAh, tAl, tBh, tBl, p);
+    else gemm_tf32x3_kernel<1><<<grid, THREADS, Cfg<1>::SMEM, st>>>(tAh, tAl, tBh, tBl, p);
     e = cudaGetLastError();
     cudaFreeAsync(ws, st);
     if (e != cudaSuccess) { if (ws_c) cudaFreeAsync(ws_c, st); return set_error("gemm_tf32x3 launch failed: %s", cudaGetErrorString(e)); }
