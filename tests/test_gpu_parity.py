@@ -656,3 +656,23 @@ def test_elementwise_iteration_space_splitting(ad):
     check(got[1], onp.Tanh(onp.Variable(flat))())
     check(got[2], x[0].T @ y[0])
     check(got[3], x * b)
+
+
+def test_negative_and_odd_strides_everywhere(ad):
+    """Reversed / stepped slices (negative and non-unit strides, odd offsets) through elementwise, reduction and
+    contraction kernels: everything falls back to the scalar-access or generic paths and must still be exact."""
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((40, 70)); y = rng.standard_normal((40, 70))
+    X, Y = ad.Variable(x, name="x"), ad.Variable(y, name="y")
+    xr, yr = X[::-1, ::-1], Y[::-1, 1::2]
+    check((xr * 2.0 + X)(), x[::-1, ::-1] * 2.0 + x)
+    check(ad.Exp(yr)(), np.exp(y[::-1, 1::2]))
+    check(ad.Einsum("ab->a", xr)(), x[::-1, ::-1].sum(1))
+    check(ad.Einsum("ab->b", yr)(), y[::-1, 1::2].sum(0))
+    check(ad.Einsum("ab->", X[3:37:3, 5::7])(), x[3:37:3, 5::7].sum())
+    check((xr @ ad.Transpose(X))(), x[::-1, ::-1] @ x.T)
+    check(ad.Einsum("ab,cb->ac", X[:, ::-1], Y[::2])(), x[:, ::-1] @ y[::2].T)
+    z = rng.standard_normal((9, 6, 5, 7))
+    Z = ad.Variable(z, name="z")
+    check(ad.Einsum("abcd->ca", Z[::-1, :, ::2])(), np.einsum("abcd->ca", z[::-1, :, ::2]))
+    check(ad.Tanh(Z[1:, ::-1, :, 1:6])(), onp.Tanh(onp.Variable(z[1:, ::-1, :, 1:6]))())
