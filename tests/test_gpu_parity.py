@@ -676,3 +676,37 @@ def test_negative_and_odd_strides_everywhere(ad):
     Z = ad.Variable(z, name="z")
     check(ad.Einsum("abcd->ca", Z[::-1, :, ::2])(), np.einsum("abcd->ca", z[::-1, :, ::2]))
     check(ad.Tanh(Z[1:, ::-1, :, 1:6])(), onp.Tanh(onp.Variable(z[1:, ::-1, :, 1:6]))())
+
+
+def test_baseline_size_contractions_vs_blas(ad):
+    """FULL BASELINE sizes against a BLAS-backed numpy restatement (SURVEY 8d "Parity": np.matmul agrees with the true
+    np.einsum path to rounding at the sizes where both can run, see test_einsum_forward_and_grads_vs_oracle): the C2a
+    forward product and both gradient forms at 8192^2, one C3 layer (8192 x 4097 x 4096, ragged K) and the C2b batch at
+    64 x 1024^2, each within 1e-12 norm-wise."""
+    rng = np.random.default_rng(99)
+    n = 8192
+    a = rng.standard_normal((n, n)); b = rng.standard_normal((n, n))
+    A, B = ad.Variable(ad.to_device(a), name="A"), ad.Variable(ad.to_device(b), name="B")
+    e = ad.Einsum("ij,jk->ik", A, B)
+    da, db = ad.grad(e, [A, B])
+    got = ad.eval_many([e, da, db])
+    check(got[0], a @ b, tol=1e-12, what="C2a fwd")
+    ones = np.ones((n, n))
+    check(got[1], ones @ b.T, tol=1e-12, what="C2a dA")
+    check(got[2], a.T @ ones, tol=1e-12, what="C2a dB")
+    del got, e, da, db, A, B, ones
+    x = rng.standard_normal((8192, 4097)); w = rng.standard_normal((4097, 4096)) * 0.01
+    check((ad.Variable(x, name="x") @ ad.Variable(w, name="w"))(), x @ w, tol=1e-12, what="C3 layer")
+    p = rng.standard_normal((64, 1024, 1024)); q = rng.standard_normal((64, 1024, 1024))
+    check(ad.Einsum("bij,bjk->bik", ad.Variable(p, name="p"), ad.Variable(q, name="q"))(), np.matmul(p, q), tol=1e-12, what="C2b fwd")
+    del p, q, x, w
+    # C2c at full size (128^4): the HBM-bound members against np.einsum itself (the reference's call, ops.py:180)
+    t4 = rng.standard_normal((128, 128, 128, 128)); m2 = rng.standard_normal((128, 128)); g2 = rng.standard_normal((128, 128))
+    T4 = ad.Variable(ad.to_device(t4), name="T")
+    check(ad.Einsum("ijkl,jl->ik", T4, ad.Variable(m2, name="m"))(), np.einsum("ijkl,jl->ik", t4, m2), tol=1e-12, what="C2c fwd")
+    check(ad.Einsum("ijkl,ik->jl", T4, ad.Variable(g2, name="g"))(), np.einsum("ijkl,ik->jl", t4, g2), tol=1e-12, what="C2c dB")
+    del T4, t4
+    outer = ad.Einsum("ik,jl->ijkl", ad.Variable(g2, name="g"), ad.Variable(m2, name="m"))()
+    assert outer.shape == (128, 128, 128, 128)
+    assert np.array_equal(outer[5, :, 7, :], g2[5, 7] * m2) and np.array_equal(outer[:, 100, :, 3], g2 * m2[100, 3])
+    assert abs(outer.sum() - g2.sum() * m2.sum()) <= 1e-9 * abs(g2.sum() * m2.sum()) + 1e-6
