@@ -52,6 +52,9 @@ using CfgSmall = TileCfg<64, 64, 6, 2>;
 // Tall-and-skinny problems (im2col convolutions: M = batch*OH*OW, N = output channels <= 32): all 8 warps stack along M
 // and share the whole 32-column B tile, so no MMA work is spent on padding columns.
 using CfgSkinny = TileCfg<256, 32, 6, 1, 8, 1>;
+// Few rows AND few columns with a long K (weight gradients of the first conv layer: 75 x 16 x 921600): 128x32 tiles,
+// two CTAs per SM, split-K supplies the parallelism.
+using CfgSkinnyS = TileCfg<128, 32, 6, 2, 8, 1>;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = CONSUMER_WARPS * 32;   // 9 warps would round to 12 for register allocation (168 regs)
 
@@ -488,14 +491,16 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             const char* e = getenv("ADB_GEMM_TILE");
             tile_pref = !e ? 0 : (!strcmp(e, "small") ? 1 : (!strcmp(e, "big") ? 2 : 0));
         }
-        const bool skinny = force_path == 5 || (force_path == 0 && tile_pref == 0 && N <= 32 && M >= 256);
+        const bool skinny_s = force_path == 6 || (force_path == 0 && tile_pref == 0 && N <= 32 && M <= 128 && K >= 4096);
+        const bool skinny = !skinny_s && (force_path == 5 || (force_path == 0 && tile_pref == 0 && N <= 32 && M >= 256));
         // short K (<= 8 k-tiles): a CTA is mostly prologue + epilogue, so two 64x64 CTAs per SM that overlap each other beat
         // one 128x128 CTA (conv dX 802816x400x32: 1.38 -> 1.05 ms)
         const bool short_k = (K + BK - 1) / BK <= 8;
-        const bool small = !skinny && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && (waste_big > 1.05 || short_k)))));
-        const int bm = skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM, bn = skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
+        const bool small = !skinny && !skinny_s && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && (waste_big > 1.05 || short_k)))));
+        const int bm = skinny_s ? CfgSkinnyS::BM : skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM;
+        const int bn = skinny_s ? CfgSkinnyS::BN : skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
-        const long long slots = small ? 296 : 148;
+        const long long slots = (small || skinny_s) ? 296 : 148;
         const int total_kt = (int)((K + BK - 1) / BK);
         int splits = 1;
         if (tiles * 2 <= slots && total_kt >= 32) {
@@ -527,7 +532,12 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
             int rc;
-            if (skinny) {
+            if (skinny_s) {
+                if (a_kc && b_kc) rc = launch_tma<CfgSkinnyS, true, true>(ta, tb, p, (int)batch, splits, st);
+                else if (a_kc && !b_kc) rc = launch_tma<CfgSkinnyS, true, false>(ta, tb, p, (int)batch, splits, st);
+                else if (!a_kc && b_kc) rc = launch_tma<CfgSkinnyS, false, true>(ta, tb, p, (int)batch, splits, st);
+                else rc = launch_tma<CfgSkinnyS, false, false>(ta, tb, p, (int)batch, splits, st);
+            } else if (skinny) {
                 if (a_kc && b_kc) rc = launch_tma<CfgSkinny, true, true>(ta, tb, p, (int)batch, splits, st);
                 else if (a_kc && !b_kc) rc = launch_tma<CfgSkinny, true, false>(ta, tb, p, (int)batch, splits, st);
                 else if (!a_kc && b_kc) rc = launch_tma<CfgSkinny, false, true>(ta, tb, p, (int)batch, splits, st);

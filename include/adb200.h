@@ -66,7 +66,8 @@ ADB_API int adb_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, 
 /* ---- contraction: replaces np.einsum at reference autodiff/core/ops.py:180 ---------------------- */
 ADB_API int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
 /* path: 0 = auto, 1 = force TMA+DMMA kernel (error if not describable), 2 = force generic kernel,
- * 3 = force TMA+DMMA with 64x64 tiles, 4 = force TMA+DMMA with 128x128 tiles, 5 = force the 256x32 tall-skinny tiles */
+ * 3 = force TMA+DMMA with 64x64 tiles, 4 = force TMA+DMMA with 128x128 tiles, 5 = force the 256x32 tall-skinny tiles,
+ * 6 = force the 128x32 tiles (few rows and few columns, long K) */
 ADB_API int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
 /* Same contract (fp64 in, fp64 out), arithmetic as 3xTF32 on the tcgen05 tensor cores with fp32 accumulation in TMEM:
  * a ~= hi + lo, A.B ~= hi.hi + lo.hi + hi.lo  (parity bar 1e-4; measured ~1e-7). */

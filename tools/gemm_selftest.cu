@@ -218,6 +218,10 @@ int main(int argc, char** argv) {
             fails += run_case(Case{s[1], s[0], s[2], s[3], a, b, 0, 0}, false, 0);   // few rows, many columns: swapped roles
         }
         fails += run_case(Case{400, 32, 50000, 1, a, b, 0, 5}, false, 0);            // skinny + split-K
+        fails += run_case(Case{75, 16, 30000, 1, a, b, 0, 6}, false, 0);             // 128x32 tiles + split-K
+        fails += run_case(Case{75, 16, 30000, 1, a, b, 0, 0}, false, 0);
+        fails += run_case(Case{128, 32, 4096, 2, a, b, 0, 6}, false, 0);
+        fails += run_case(Case{100, 30, 5000, 1, a, b, 0, 0}, false, 0);
     }
     printf("correctness: %d failing cases\n", fails);
     if (argc > 1 && !strcmp(argv[1], "rnn")) {            // char-rnn (C5) shapes under every tile configuration
@@ -247,6 +251,8 @@ int main(int argc, char** argv) {
         run_case(Case{400, 32, 802816, 1, 0, 0, 0, 5}, true, 3);   // conv2 dW, skinny + split-K
         run_case(Case{75, 16, 921600, 1, 0, 0, 0, 0}, true, 3);    // conv1 dW
         run_case(Case{75, 16, 921600, 1, 0, 0, 0, 5}, true, 3);
+        run_case(Case{75, 16, 921600, 1, 0, 0, 0, 6}, true, 3);
+        run_case(Case{75, 16, 921600, 1, 0, 0, 0, 3}, true, 3);
         run_case(Case{512, 71, 1024, 1, 1, 0, 0, 0}, true, 3);     // char-rnn logits
         return fails ? 1 : 0;
     }
