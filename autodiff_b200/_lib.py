@@ -66,6 +66,12 @@ PROTOTYPES = {
     "adb_softmax_ce": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "adb_im2col": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
     "adb_col2im": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
+    "adb_graph_begin": (C.c_int, [C.c_void_p]),
+    "adb_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "adb_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "adb_graph_destroy": (C.c_int, [C.c_void_p]),
+    "adb_memset_async": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "adb_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libadb200.so")
 EW_NSHARDS = 4   # must match N_SHARDS in tools/gen_ewise_catalog.py
 # (source, extra nvcc flags, object name)
 SOURCES = [(f, [], f.replace(".cu", ".o")) for f in
-           ["adb_core.cu", "gemm_f64.cu", "gemm_tf32x3.cu", "ewise.cu", "reduce.cu", "einsum.cu", "conv.cu"]]
+           ["adb_core.cu", "gemm_f64.cu", "gemm_tf32x3.cu", "ewise.cu", "reduce.cu", "softmax_ce_ring.cu", "einsum.cu", "conv.cu"]]
 SOURCES += [("ewise_catalog.cu", ["-DEW_SHARD=%d" % k], "ewise_catalog_%d.o" % k) for k in range(EW_NSHARDS)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -16,12 +16,21 @@ The tape removes that work for every evaluation after the second one of a given 
            and re-issue the calls (the C++ side re-plans tiles / access modes from the actual pointers, so alignment or
            workspace differences are handled there), then hand every materialised node a `DeviceArray` view of the arena.
 
+  graph    from the 2nd replay on, a tape whose leaves are small (<= 64 MB) is replayed as ONE CUDA graph: the recorded calls
+           are issued once more on a side stream in capture mode (C ABI adb_graph_begin / adb_graph_end) against a buffer
+           the tape keeps - [copies of the leaf storages | arena] - and every later replay is: copy the leaves into their
+           staging area, one `cudaGraphLaunch`.  The launch-bound configs (C1: 25 kernels, C5: 10 k kernels) then cost one
+           driver call per step instead of one ctypes call + planner pass per kernel.  The buffer is reused only when no
+           `DeviceArray` of the previous replay is still alive (refcount of the buffer tensor); otherwise, and whenever
+           capture fails, the replay falls back to the call-by-call path above.  `ADB_TAPE_GRAPH=0` disables it.
+
 Results are bit-identical to the normal path: the same kernels run on the same operands in the same order.  Graphs with
 user-defined numpy nodes, unknown node classes or unresolvable pointers are simply never taped.  `ADB_TAPE=0` disables it.
 """
 import bisect
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -38,12 +47,17 @@ SELF_CHECK = os.environ.get("ADB_TAPE_SELFCHECK", "0") == "1"
 if SELF_CHECK:
     RECORD_AT = 1
 MAX_TAPES = 64
+GRAPH = os.environ.get("ADB_TAPE_GRAPH", "1") != "0"
+GRAPH_AFTER_REPLAYS = int(os.environ.get("ADB_TAPE_GRAPH_AFTER", "1"))   # call-by-call replays before a tape is captured (0 with
+GRAPH_MIN_CALLS = int(os.environ.get("ADB_TAPE_GRAPH_MIN_CALLS", "4"))   # ADB_TAPE_SELFCHECK=1: every graph of the test-suite)
+GRAPH_MAX_STAGE_BYTES = 64 << 20       # leaves are copied next to the arena on every replay: only worth it when they are small
 SCE_ERROR = "Labels must be a valid probability distribution!"
 
 _seen = {}               # signature -> sightings so far
 _tapes = {}              # signature -> Tape | False (not tapeable)
 _recorder = None         # active Recorder (set while a recording evaluation runs)
-stats = {"replays": 0, "records": 0, "rejected": 0}
+stats = {"replays": 0, "records": 0, "rejected": 0, "graphs": 0, "graph_launches": 0, "graph_rejected": 0, "graph_busy": 0}
+_cap_stream = None       # side stream the graphs are captured on (the legacy default stream cannot be captured)
 
 # node classes whose device evaluation is a pure function of (class, these attributes, children): filled by register()
 _ATTRS = {}
@@ -151,7 +165,21 @@ class _Call:
 
 
 class Tape:
-    __slots__ = ("n_nodes", "n_ext", "ext_leaf", "leaf_ext", "abs_keep", "slot_off", "arena_elems", "calls", "top_ends", "values")
+    __slots__ = ("n_nodes", "n_ext", "ext_leaf", "leaf_ext", "abs_keep", "slot_off", "arena_elems", "calls", "top_ends", "values",
+                 "ext_size", "replays", "graph")
+
+
+class _Graph:
+    """One captured replay: the cudaGraphExec_t, the buffer its kernels address ([leaf staging | arena]) and its flags."""
+    __slots__ = ("exec", "buf", "refs", "stage_off", "arena_off", "flags", "nflags")
+
+    def __del__(self):
+        ex = getattr(self, "exec", None)
+        if ex:
+            try:
+                _lib.lib().adb_graph_destroy(ex)
+            except Exception:
+                pass
 
 
 def _tensor_structs(arg):
@@ -263,7 +291,123 @@ def build_tape(rec, order, leaves, n_tops):
     tape.slot_off, tape.arena_elems = slot_off, total
     tape.top_ends = list(rec.top_ends)
     tape.values = values
+    tape.ext_size, tape.replays, tape.graph = ext_size, 0, None
     return tape
+
+
+# ------------------------------------------------------------------------------------------------ CUDA-graph replay
+def _capture(tape):
+    """Issues the tape's calls against a private buffer: once eagerly on the capture stream (sizes every grow-only
+    workspace of the library for that stream, so nothing allocates while recording), once in capture mode."""
+    global _cap_stream
+    t = torch()
+    L = _lib.lib()
+    g = _Graph()
+    g.exec = None
+    g.stage_off, total = [], 0
+    for sz in tape.ext_size:
+        g.stage_off.append(total)
+        total += (sz // 8 + 31) // 32 * 32
+    g.arena_off = total
+    g.buf = t.empty(total + max(tape.arena_elems, 2), dtype=t.float64, device="cuda")
+    g.nflags = sum(1 for c in tape.calls if c.flag_arg >= 0)
+    g.flags = t.zeros(max(g.nflags, 1), dtype=t.int32, device="cuda")
+    if _cap_stream is None:
+        _cap_stream = t.cuda.Stream()
+    _cap_stream.wait_stream(t.cuda.current_stream())
+    b0, f0 = g.buf.data_ptr(), g.flags.data_ptr()
+    bases = [b0 + 8 * o for o in g.stage_off] + [b0 + 8 * (total + o) for o in tape.slot_off]
+    sp = C.c_void_p(_cap_stream.cuda_stream)
+    check = _lib.check
+
+    def issue():
+        fi = 0
+        for c in tape.calls:
+            for ts, j, off in c.patches:
+                ts.ptr = bases[j] + off
+            args = list(c.args)
+            for ai, j, off in c.void_patches:
+                args[ai] = C.c_void_p(bases[j] + off)
+            args[-1] = sp                         # every compute entry point takes the stream last
+            if c.flag_arg >= 0:
+                fp = C.c_void_p(f0 + 4 * fi)
+                fi += 1
+                check(L.adb_memset_async(fp, 0, 4, sp))      # part of the graph: each launch starts from a clean flag
+                args[c.flag_arg] = fp
+            check(c.fn(*args))
+    try:
+        issue()
+        check(L.adb_sync(sp))
+        check(L.adb_graph_begin(sp))
+        ex = C.c_void_p()
+        try:
+            issue()
+        except Exception:
+            L.adb_graph_end(sp, C.byref(ex))      # leave capture mode; the partial recording is dropped
+            if ex.value:
+                L.adb_graph_destroy(ex)
+            raise
+        check(L.adb_graph_end(sp, C.byref(ex)))
+    except (_lib.BackendError, ValueError):
+        stats["graph_rejected"] += 1
+        return False
+    g.exec = ex
+    g.refs = sys.getrefcount(g.buf)
+    stats["graphs"] += 1
+    return g
+
+
+def _graph_for(tape, base_tensors):
+    """The tape's graph if this replay may use it, else None (call-by-call replay)."""
+    g = tape.graph
+    if g is False or not GRAPH:
+        return None
+    for j, b in enumerate(base_tensors):
+        if b.numel() * 8 != tape.ext_size[j]:
+            return None                           # a leaf that is now a view of a differently sized array
+    if g is None:
+        if tape.replays <= GRAPH_AFTER_REPLAYS or len(tape.calls) < GRAPH_MIN_CALLS or sum(tape.ext_size) > GRAPH_MAX_STAGE_BYTES:
+            return None
+        g = tape.graph = _capture(tape)
+        if g is False:
+            return None
+    if sys.getrefcount(g.buf) > g.refs:
+        stats["graph_busy"] += 1                  # a value of the previous replay is still alive in the buffer
+        return None
+    return g
+
+
+def _launch_graph(tape, g, order, bases, base_tensors, tops, add_pending_flag, on_ready):
+    L = _lib.lib()
+    check = _lib.check
+    t = torch()
+    if g.nflags:
+        from . import engine
+        if engine._pending_flags:
+            engine.check_pending_flags()          # the flags of the previous launch are about to be re-zeroed
+    st = C.c_void_p(_device.stream_ptr())
+    b0 = g.buf.data_ptr()
+    for j, off in enumerate(g.stage_off):
+        check(L.adb_memcpy_d2d(C.c_void_p(b0 + 8 * off), C.c_void_p(bases[j]), tape.ext_size[j], st))
+    check(L.adb_graph_launch(g.exec, st))
+    n_ext, slot_off, a0, buf = tape.n_ext, tape.slot_off, g.arena_off, g.buf
+    make = DeviceArray._make
+    for i, j, off, shape, strides in tape.values:
+        n = order[i]
+        if j >= n_ext:
+            n._dev = make(buf, a0 + slot_off[j - n_ext] + off, shape, strides)
+        elif j >= 0:
+            n._dev = make(base_tensors[j], off, shape, strides)
+        else:
+            n._dev = off
+    for k in range(g.nflags):
+        add_pending_flag(g.flags[k:k + 1], ValueError(SCE_ERROR))
+    if on_ready is not None:
+        for top in tops:
+            on_ready(top)
+    stats["replays"] += 1
+    stats["graph_launches"] += 1
+    return True
 
 
 # ------------------------------------------------------------------------------------------------ replay
@@ -283,6 +427,10 @@ def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
         d = leaves[i]._dev
         if d.base.data_ptr() != bases[j] or d.offset != off:
             return False                          # e.g. two leaves that were views of one array are now separate arrays
+    tape.replays += 1
+    g = _graph_for(tape, base_tensors)
+    if g is not None:
+        return _launch_graph(tape, g, order, bases, base_tensors, tops, add_pending_flag, on_ready)
     arena = t.empty(max(tape.arena_elems, 2), dtype=t.float64, device="cuda")
     a0 = arena.data_ptr()
     for off in tape.slot_off:

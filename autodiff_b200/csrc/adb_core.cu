@@ -100,4 +100,50 @@ int adb_host_free(void* ptr) {
     return 0;
 }
 
+int adb_memset_async(void* ptr, int byte_value, size_t bytes, void* stream) {
+    if (!bytes) return 0;
+    ADB_CUDA_OK(cudaMemsetAsync(ptr, byte_value, bytes, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!bytes) return 0;
+    ADB_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// ---- CUDA-graph replay of launch tapes (core/tape.py).  Relaxed mode: the planner may call cudaMalloc / cudaFuncSetAttribute
+// while a recording is open (workspaces are warmed up by an eager pass first, so in practice it does not).
+int adb_graph_begin(void* capture_stream) {
+    if (!capture_stream) return adb::set_error("adb_graph_begin: the legacy default stream cannot be captured");
+    ADB_CUDA_OK(cudaStreamBeginCapture(reinterpret_cast<cudaStream_t>(capture_stream), cudaStreamCaptureModeRelaxed));
+    return 0;
+}
+int adb_graph_end(void* capture_stream, void** exec) {
+    *exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(reinterpret_cast<cudaStream_t>(capture_stream), &graph);
+    if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        return adb::set_error("adb_graph_end: capture failed (%s)", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return adb::set_error("adb_graph_end: cudaGraphInstantiate failed (%s)", cudaGetErrorString(e));
+    }
+    *exec = ex;
+    return 0;
+}
+int adb_graph_launch(void* exec, void* stream) {
+    ADB_CUDA_OK(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(exec), reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int adb_graph_destroy(void* exec) {
+    if (exec) ADB_CUDA_OK(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec)));
+    return 0;
+}
+
 }  // extern "C"

@@ -21,6 +21,7 @@
 #include <mutex>
 
 #include "adb_internal.h"
+#include "adb_math.cuh"
 
 namespace adb {
 
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const double* __restric
         if (__any_sync(0xffffffffu, nan_seen)) mx = NAN;      // np.max propagates NaN
         double se = 0.0, lsum = 0.0;
         for (long long c = lane; c < cols; c += 32) {
-            se += exp(__ldg(z + c * z_sc) - mx);
+            se += exp_nonpos(__ldg(z + c * z_sc) - mx);
             lsum += __ldg(l + c * l_sc);
         }
 #pragma unroll
@@ -785,13 +786,12 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
-            if (c < cols) {
-                if (m != -INFINITY) se += exp(zq[k].v[e] - m);
-                dot += lq[k].v[e] * zq[k].v[e];
-            }
-            lsum += lq[k].v[e];
+            se += exp_nonpos(zq[k].v[e] - m);          // straight-line (no branch per element): the 4K evaluations interleave.
+            dot += c < cols ? lq[k].v[e] * zq[k].v[e] : 0.0;   // Padding is -inf -> 0; a warp of only -inf (m = -inf) yields NaN
+            lsum += lq[k].v[e];                        // here and is discarded by the M == -inf test of the combine below
         }
     }
+    if (m == -INFINITY) se = 0.0;              // nothing but -inf (or padding) in this warp: contributes no mass
     if (has_nan) se = NAN;                     // np.max propagates NaN (fmax does not)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
         double Mx = M;
 #pragma unroll
         for (int off = NW / 2; off > 0; off >>= 1) Mx = fmax(Mx, __shfl_xor_sync(0xffffffffu, Mx, off));
-        S = (M == -INFINITY) ? 0.0 : S * exp(M - Mx);
+        S = (M == -INFINITY) ? S : S * exp_nonpos(M - Mx);    // (S is 0, or NaN when the warp saw a NaN, for M = -inf)
         M = Mx;
 #pragma unroll
         for (int off = NW / 2; off > 0; off >>= 1) {
@@ -834,6 +834,11 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
 // copies - was measured at 0.47 of the HBM roof against 0.66 for the kernel above: with 64 KB per row only one CTA fits
 // per SM, and the per-row dependent chain (max -> exp -> sum -> log) then has no second CTA to overlap with.)
 
+static bool sce_ring_enabled() {                 // ADB_SCE_RING=0 pins the register-resident kernels (A/B measurements, tests)
+    const char* e = getenv("ADB_SCE_RING");
+    return !(e && e[0] == '0');
+}
+
 int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st) {
     if (labels->rank != 2 || logits->rank != 2) return set_error("softmax_ce: labels and logits must be 2-D (got %d, %d)", labels->rank, logits->rank);
     const long long rows = logits->shape[0], cols = logits->shape[1];
@@ -842,6 +847,10 @@ int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb
     if (rows == 0) return 0;
     const bool quad_ok = labels->stride[1] == 1 && logits->stride[1] == 1 && aligned32(labels->ptr) && aligned32(logits->ptr) &&
                          labels->stride[0] % 4 == 0 && logits->stride[0] % 4 == 0;
+    if (quad_ok && sce_ring_enabled()) {
+        const int r = softmax_ce_ring_try(labels, logits, out, flag, st);     // persistent ring kernel (softmax_ce_ring.cu)
+        if (r >= 0) return r;
+    }
     if (quad_ok && cols >= 512 && cols <= 8192 && rows < (1LL << 31)) {
         const unsigned g = (unsigned)rows;
 #define ADB_SCE(KK, NTT) softmax_ce_wide_kernel<KK, NTT><<<g, NTT, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \

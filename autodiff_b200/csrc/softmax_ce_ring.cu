@@ -1,0 +1,208 @@
+// SoftmaxCEWithLogits (reference autodiff/core/ops.py:243-255) for wide rows, decoupled-load variant.
+//
+// Why a second kernel: `softmax_ce_wide_kernel` (reduce.cu) keeps a row in registers, so a CTA alternates between a
+// load phase and an FP64 phase (one exp per element: ~0.6 of the HBM time at 8192x4096).  The two resident CTAs of an
+// SM fall into lock-step - both load, then both compute - and HBM idles during every compute phase (0.67 of the roof).
+// Here the loads never stop:
+//   * one persistent CTA per SM made of GROUPS independent groups of 128 threads; the rows of the CTA go to the groups
+//     round-robin, and every group owns SPG slots of a shared-memory ring (192 KB in total: 3 x 64 KB at 4096 columns);
+//   * a row reaches its slot by two 1-D bulk copies (`cp.async.bulk.shared::cluster.global.mbarrier::complete_tx`), logits
+//     and labels.  The group drains the slot into registers - the labels are folded into sum(l) and sum(l*z) on the way
+//     and never kept - and its thread 0 immediately re-arms the slot with the group's next row, so a slot is idle for
+//     ~0.3 us of the ~1.5 us a row costs at the HBM rate and 2-3 rows per SM are in flight at all times;
+//   * the dependent chain of a row (max -> exp -> sum -> log) then runs out of registers while the next row streams in,
+//     and the groups sit at different points of it, which keeps the FP64 pipe busy.
+// Per row and group: two 128-thread named barriers (slot drained; warp results exchanged).  Arithmetic is the same online
+// log-sum-exp as the wide kernel: each warp reduces to (max, sum exp(z - max), sum l, sum l*z), the four warp results are
+// rescaled to the row max with one exp each;  out = -(sum l*z - lse * sum l).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "adb_internal.h"
+#include "adb_math.cuh"
+
+namespace adb {
+namespace {
+
+constexpr int SCE_RING_BYTES = 192 * 1024;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+template <int GT>
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory");
+}
+
+// GT threads per group, P = 16-byte pairs per thread: columns <= GT * 2 * P.  GROUPS * SPG slots of 2 * row_bytes each.
+template <int P, int GROUPS, int SPG, int GT>
+__global__ void __launch_bounds__(GROUPS * GT, 1)
+softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits, long long z_sr,
+                       double* __restrict__ out, long long o_s, long long rows, unsigned cols, unsigned row_bytes,
+                       int* __restrict__ flag) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long bars[GROUPS * SPG];
+    constexpr int NW = GT / 32;
+    __shared__ double xch[GROUPS][2][4][NW];           // [group][row parity][quantity][warp]
+    const uint32_t slot_bytes = 2u * row_bytes;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < GROUPS * SPG; ++s) bar_init(s_u32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    // rows of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; the j-th of them belongs to group j % GROUPS, and the k-th
+    // row of a group (j = g + k * GROUPS) uses the group's slot k % SPG
+    const long long first = blockIdx.x, step = gridDim.x;
+    const long long mine = first < rows ? (rows - first + step - 1) / step : 0;
+    const int g = threadIdx.x / GT, t = threadIdx.x % GT, w = t >> 5, lane = t & 31;
+    const long long gmine = mine > g ? (mine - g + GROUPS - 1) / GROUPS : 0;
+    unsigned char* const gring = ring + (size_t)g * SPG * slot_bytes;
+    const uint32_t gbar = s_u32(bars + g * SPG);
+
+    auto arm = [&](long long k) {                      // thread 0 of the group: start the copies of the group's k-th row
+        const int s = (int)(k % SPG);
+        const long long r = first + (g + k * GROUPS) * step;
+        const uint32_t dst = s_u32(gring) + s * slot_bytes;
+        bar_expect_tx(gbar + 8 * s, slot_bytes);
+        bulk_load(dst, logits + r * z_sr, row_bytes, gbar + 8 * s);
+        bulk_load(dst + row_bytes, labels + r * l_sr, row_bytes, gbar + 8 * s);
+    };
+    if (t == 0) {
+        for (long long k = 0; k < SPG && k < gmine; ++k) arm(k);
+    }
+    for (long long k = 0; k < gmine; ++k) {
+        const int s = (int)(k % SPG);
+        bar_wait(gbar + 8 * s, (uint32_t)(k / SPG) & 1u);
+        const double2* zs = reinterpret_cast<const double2*>(gring + (size_t)s * slot_bytes);
+        const double2* ls = reinterpret_cast<const double2*>(gring + (size_t)s * slot_bytes + row_bytes);
+        double z[2 * P];
+        double lsum = 0.0, dot = 0.0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const unsigned c = 2u * (p * GT + t);
+            double2 zv = make_double2(-INFINITY, -INFINITY), lv = make_double2(0.0, 0.0);
+            if (c < cols) { zv = zs[p * GT + t]; lv = ls[p * GT + t]; }
+            if (c + 1 >= cols) { zv.y = -INFINITY; lv.y = 0.0; }      // odd width: the pair's second half is row padding
+            z[2 * p] = zv.x; z[2 * p + 1] = zv.y;
+            if (c < cols) dot += lv.x * zv.x;
+            if (c + 1 < cols) dot += lv.y * zv.y;
+            lsum += lv.x;
+            lsum += lv.y;
+        }
+        group_sync<GT>(g);                             // the slot is drained: everything the row needs is in registers
+        if (t == 0 && k + SPG < gmine) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            arm(k + SPG);
+        }
+        double m = -INFINITY;
+        bool has_nan = false;
+#pragma unroll
+        for (int e = 0; e < 2 * P; ++e) { m = fmax(m, z[e]); has_nan |= z[e] != z[e]; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        double se = 0.0;
+#pragma unroll
+        for (int e = 0; e < 2 * P; ++e) se += exp_nonpos(z[e] - m);   // straight-line: the 2P evaluations interleave; padding: exp(-inf) = 0
+        if (m == -INFINITY) se = 0.0;                  // nothing but -inf (or padding) in this warp: (-inf) - (-inf) gave NaN above
+        if (has_nan) se = NAN;                         // np.max propagates NaN (fmax does not)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, off);
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+            dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        }
+        double (*x)[NW] = xch[g][k & 1];
+        if (lane == 0) { x[0][w] = m; x[1][w] = se; x[2][w] = lsum; x[3][w] = dot; }
+        group_sync<GT>(g);
+        if (w == 0) {
+            double M = x[0][lane % NW], S = x[1][lane % NW], L = x[2][lane % NW], D = x[3][lane % NW];
+            double Mx = M;
+#pragma unroll
+            for (int off = 1; off < NW; off <<= 1) Mx = fmax(Mx, __shfl_xor_sync(0xffffffffu, Mx, off));
+            S = (M == -INFINITY) ? S : S * exp_nonpos(M - Mx);      // (S is 0, or NaN when the warp saw a NaN, for M = -inf)
+#pragma unroll
+            for (int off = 1; off < NW; off <<= 1) {
+                S += __shfl_xor_sync(0xffffffffu, S, off);
+                L += __shfl_xor_sync(0xffffffffu, L, off);
+                D += __shfl_xor_sync(0xffffffffu, D, off);
+            }
+            if (lane == 0) {
+                if (Mx == -INFINITY) S = NAN;          // a row of -inf: numpy computes exp(-inf - -inf) = nan
+                const double lse = Mx + log(S);
+                out[(first + (g + k * GROUPS) * step) * o_s] = -(D - lse * L);
+                if (!(fabs(L - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+            }
+        }
+    }
+}
+
+template <int P, int GROUPS, int SPG, int GT>
+cudaError_t launch_ring(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st,
+                        unsigned grid, unsigned row_bytes) {
+    static bool attr_set = false;                      // one host thread per device
+    const int smem = GROUPS * SPG * 2 * (int)row_bytes;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(softmax_ce_ring_kernel<P, GROUPS, SPG, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCE_RING_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    softmax_ce_ring_kernel<P, GROUPS, SPG, GT><<<grid, GROUPS * GT, smem, st>>>(
+        static_cast<const double*>(labels->ptr), labels->stride[0], static_cast<const double*>(logits->ptr), logits->stride[0],
+        static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], (unsigned)logits->shape[1], row_bytes, flag);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Returns 0 = launched, 1 = error (set_error called), -1 = not applicable (the caller uses the register-resident kernels).
+// Preconditions checked by the caller: 2-D, unit column stride, 32-byte aligned bases, row strides multiples of 4.
+int softmax_ce_ring_try(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st) {
+    const long long rows = logits->shape[0], cols = logits->shape[1];
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // Measured per width (tools/bench_sce.py, profiles/r01_softmax_ce_ab.log): the ring wins where a row is too big for two
+    // resident register-kernel CTAs to overlap (2048 < cols <= 4096: 0.83 vs 0.60-0.75 of the HBM roof); up to 2048 columns
+    // the register-resident kernel is as fast or faster (0.87 at 2048), beyond 4096 a slot pair no longer fits three times.
+    // A persistent grid also needs several rows per SM.
+    if (cols <= 2048 || cols > 4096 || rows < 4LL * sms) return -1;
+    const unsigned row_bytes = (unsigned)((cols + 1) / 2 * 16);       // whole 16-byte pairs (the tail pair may reach into the row padding)
+    const unsigned grid = (unsigned)(rows < sms ? rows : sms);
+    cudaError_t e;                                                    // slots of 2 * row_bytes fill the 192 KB ring
+    if (cols <= 3072) e = launch_ring<12, 4, 1, 128>(labels, logits, out, flag, st, grid, row_bytes);   // 4 x 48 KB
+    else e = launch_ring<16, 3, 1, 128>(labels, logits, out, flag, st, grid, row_bytes);                // 3 x 64 KB
+    if (e != cudaSuccess) return set_error("softmax_ce ring launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+}  // namespace adb

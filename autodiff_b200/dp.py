@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-from .core.engine import evaluate_many
+from .core.engine import check_pending_flags, evaluate_many
 from .core.grad import grad
 from .core.high_level_ops import NN, Adam
 from .core.node import Variable
@@ -82,6 +82,7 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True):
         if dist is not None:
             dist.all_reduce(_flat_view(lv), op=dist.ReduceOp.SUM)
         loss = float(to_host(lv))
+        check_pending_flags()                      # deferred label validation of SoftmaxCEWithLogits (reference ops.py:246-248)
     return loss
 
 

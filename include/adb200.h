@@ -158,6 +158,20 @@ ADB_API int adb_softmax_ce(const adb_tensor* labels, const adb_tensor* logits, c
 ADB_API int adb_im2col(const adb_tensor* x, int kh, int kw, const adb_tensor* cols, void* stream);
 ADB_API int adb_col2im(const adb_tensor* cols, int kh, int kw, const adb_tensor* dx, void* stream);
 
+/* ---- launch-tape replay as ONE CUDA graph (replaces the per-node Python recursion of reference
+ *      node.py:42-46 for graphs that are evaluated again and again).  adb_graph_begin puts `capture_stream` (must not be
+ *      the legacy default stream) into relaxed capture mode; every compute call issued on it afterwards is recorded
+ *      instead of executed; adb_graph_end instantiates the recording into *exec (0 and an error if a recorded call was
+ *      not capturable - the stream always leaves capture mode).  adb_graph_launch replays the whole recording with one
+ *      driver call on any stream.  adb_memset_async / adb_memcpy_d2d are the two plain stream operations the replay needs
+ *      (re-zeroing the label-check flags inside the graph, staging the leaves next to the graph's arena). */
+ADB_API int adb_graph_begin(void* capture_stream);
+ADB_API int adb_graph_end(void* capture_stream, void** exec);
+ADB_API int adb_graph_launch(void* exec, void* stream);
+ADB_API int adb_graph_destroy(void* exec);
+ADB_API int adb_memset_async(void* ptr, int byte_value, size_t bytes, void* stream);
+ADB_API int adb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

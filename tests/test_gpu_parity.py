@@ -435,6 +435,68 @@ def test_softmax_ce_wide_rows(cols, ad):
         ad.SoftmaxCEWithLogits(labels=ad.Variable(bad, name="l"), logits=ad.Variable(z, name="z"))()
 
 
+@pytest.mark.parametrize("cols", [1024, 2048, 2049, 2500, 3001, 3072, 3073, 4095, 4096])
+def test_softmax_ce_ring_rows(cols, ad):
+    """Persistent bulk-copy ring kernel (csrc/softmax_ce_ring.cu: rows >= 4 per SM, 2048 < cols <= 4096): against the oracle,
+    against the register-resident kernels (ADB_SCE_RING=0), NaN / -inf rows, label validation, pitched row views."""
+    rng = np.random.default_rng(cols)
+    rows = 4 * 148 + 41
+    z = rng.standard_normal((rows, cols)) * 4
+    lab = rng.random((rows, cols)); lab /= lab.sum(1, keepdims=True)
+
+    def run(zz, ll):
+        return ad.SoftmaxCEWithLogits(labels=ad.Variable(ll, name="l"), logits=ad.Variable(zz, name="z"))()
+    got = run(z, lab)
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    assert got.shape == ref.shape
+    check(got, ref)
+    os.environ["ADB_SCE_RING"] = "0"
+    try:
+        other = run(z, lab)
+    finally:
+        del os.environ["ADB_SCE_RING"]
+    check(got, other)
+    # a (rows, cols) window of a wider array: row pitch != cols, columns start 4 elements in
+    wide_z = rng.standard_normal((rows, cols + 12)); wide_l = rng.random((rows, cols + 12))
+    wide_l[:, 4:4 + cols] /= wide_l[:, 4:4 + cols].sum(1, keepdims=True)
+    zd, ld = ad.to_device(wide_z), ad.to_device(wide_l)
+    got_v = run(zd.getitem((slice(None), slice(4, 4 + cols))), ld.getitem((slice(None), slice(4, 4 + cols))))
+    ref_v = onp.SoftmaxCEWithLogits(labels=onp.Variable(wide_l[:, 4:4 + cols], name="l"), logits=onp.Variable(wide_z[:, 4:4 + cols], name="z"))()
+    check(got_v, ref_v)
+    z[5, 7] = np.nan
+    z[9, :] = -np.inf
+    z[11, 3] = np.inf
+    z[13, :] = -np.inf; z[13, 5] = np.nan; z[13, 200] = 1.0       # the NaN's warp holds nothing else but -inf
+    got = run(z, lab)
+    assert np.isnan(got[5]) and np.isnan(got[9]) and np.isnan(got[11]) and np.isnan(got[13])
+    assert not np.isnan(got[4]) and not np.isnan(got[rows - 1])
+    os.environ["ADB_SCE_RING"] = "0"
+    try:
+        other = run(z, lab)
+    finally:
+        del os.environ["ADB_SCE_RING"]
+    assert np.array_equal(np.isnan(other), np.isnan(got))
+    check(np.nan_to_num(got, nan=0.0, posinf=1e300, neginf=-1e300), np.nan_to_num(other, nan=0.0, posinf=1e300, neginf=-1e300))
+    bad = lab.copy(); bad[rows - 1] *= 1.01
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        run(z, bad)
+
+
+@pytest.mark.parametrize("scale", [1.0, 30.0, 300.0])
+@pytest.mark.parametrize("rows,cols", [(700, 2048), (50, 2048), (300, 71)])
+def test_softmax_ce_dynamic_range(rows, cols, scale, ad):
+    """The branch-free exp of the log-sum-exp kernels (csrc/adb_math.cuh) over arguments down to -1000s (flush to 0 below
+    exp(-700)), in all three kernels: ring (700 rows), register-resident (50 rows), warp per row (71 columns)."""
+    rng = np.random.default_rng(int(scale) + rows)
+    z = rng.standard_normal((rows, cols)) * scale
+    z[:, 0] -= 1e-3 * np.arange(rows)              # arguments just below 0 as well
+    lab = rng.random((rows, cols)); lab /= lab.sum(1, keepdims=True)
+    got = ad.SoftmaxCEWithLogits(labels=ad.Variable(lab, name="l"), logits=ad.Variable(z, name="z"))()
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    check(got, ref)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12      # element-wise too, not only norm-wise
+
+
 REDUCTIONS = [
     ("ab->a", [(300, 4096)]), ("ab->a", [(77, 1031)]), ("ab->b", [(4096, 300)]), ("ab->b", [(1031, 77)]), ("ab->b", [(9, 5000)]),
     ("ab->", [(2048, 2048)]), ("ab->", [(1, 7)]), ("a->", [(1000003,)]), ("abc->b", [(61, 130, 67)]), ("abc->ac", [(61, 130, 68)]),
@@ -564,6 +626,93 @@ def test_launch_tapes_replay_bitwise(ad):
                 assert np.array_equal(g, w), "seed %d graph %s output %d differs under the tape" % (seed, name, k)
     assert tape.stats["records"] - before["records"] >= 4, tape.stats
     assert tape.stats["replays"] - before["replays"] >= 12, tape.stats
+
+
+def test_launch_tapes_cuda_graph_replay(ad):
+    """From the 2nd replay on a small-leaf tape is ONE cudaGraphLaunch (core/tape.py): values equal the planner path bit for
+    bit on fresh data; a value of the previous replay that is still alive forces the call-by-call path (and keeps its
+    contents); the deferred label check still fires."""
+    import gc
+    from autodiff_b200.core import engine, tape
+    if not (tape.ENABLED and tape.GRAPH):
+        pytest.skip("tapes / graphs disabled")
+    tape.clear()
+    want = {}
+    tape.ENABLED = False
+    try:
+        for seed in range(7):
+            for name, nodes in _tape_graphs(ad, seed).items():
+                engine.evaluate_many(nodes)
+                want[(seed, name)] = [np.asarray(n()) for n in nodes]
+    finally:
+        tape.ENABLED = True
+    before = dict(tape.stats)
+    for seed in range(7):
+        graphs = _tape_graphs(ad, seed)
+        for name, nodes in graphs.items():
+            engine.evaluate_many(nodes)
+            for k, (n, w) in enumerate(zip(nodes, want[(seed, name)])):
+                g = np.asarray(n())
+                assert g.shape == w.shape, (seed, name, k)
+                assert np.array_equal(g, w), "seed %d graph %s output %d differs under the graph replay" % (seed, name, k)
+        del graphs, nodes, n
+        gc.collect()
+    assert tape.stats["graphs"] - before["graphs"] >= 3, tape.stats
+    assert tape.stats["graph_launches"] - before["graph_launches"] >= 9, tape.stats
+    # a survivor of the previous replay pins the graph's buffer: the next replay must not overwrite it
+    keep = _tape_graphs(ad, 100)["mlp"]
+    engine.evaluate_many(keep)
+    kept_dev = keep[0].eval_device()
+    kept_val = ad.to_host(kept_dev).copy()
+    busy = tape.stats["graph_busy"]
+    nxt = _tape_graphs(ad, 101)["mlp"]
+    engine.evaluate_many(nxt)
+    assert tape.stats["graph_busy"] == busy + 1
+    assert np.array_equal(ad.to_host(kept_dev), kept_val)
+    ref = _tape_graphs(ad, 101)["mlp"]
+    tape.ENABLED = False
+    try:
+        engine.evaluate_many(ref)
+    finally:
+        tape.ENABLED = True
+    for a, b in zip(nxt, ref):
+        assert np.array_equal(np.asarray(a()), np.asarray(b()))
+
+
+def test_launch_tapes_cuda_graph_label_flag(ad):
+    from autodiff_b200.core import engine, tape
+    if not (tape.ENABLED and tape.GRAPH):
+        pytest.skip("tapes / graphs disabled")
+    tape.clear()
+    rng = np.random.default_rng(6)
+
+    def build(bad=False):
+        z = rng.standard_normal((8, 5)); lab = np.eye(5)[rng.integers(0, 5, 8)]
+        if bad:
+            lab[3] *= 2.0
+        Z, Lb = ad.Variable(z, name="z"), ad.Variable(lab, name="l")
+        sce = ad.SoftmaxCEWithLogits(labels=Lb, logits=ad.Exp(Z * 0.5) + Z)
+        parts = [ad.Einsum("i->", sce * float(k + 1)) for k in range(4)]      # enough kernels for a graph
+        return z, lab, sce, parts
+    for i in range(6):
+        z, lab, sce, parts = build()
+        engine.evaluate_many(parts + [sce])
+        ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab), logits=onp.Variable(np.exp(z * 0.5) + z))()
+        check(sce(), ref)
+        for k in range(4):
+            check(parts[k](), ref.sum() * (k + 1))
+        del sce, parts                              # (a surviving node would pin the graph's buffer: see the test above)
+    assert tape.stats["graph_launches"] >= 2, tape.stats
+    z, lab, sce, parts = build(bad=True)
+    launches = tape.stats["graph_launches"]
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        engine.evaluate_many(parts + [sce])
+        parts[0]()
+    assert tape.stats["graph_launches"] == launches + 1
+    del sce, parts
+    z, lab, sce, parts = build()                   # and the flag is clean again on the next launch
+    engine.evaluate_many(parts + [sce])
+    check(sce(), onp.SoftmaxCEWithLogits(labels=onp.Variable(lab), logits=onp.Variable(np.exp(z * 0.5) + z))())
 
 
 def test_launch_tapes_intermediates_flags_and_callbacks(ad):

@@ -126,11 +126,26 @@ timeit("pitched relu 8192x4097", lambda: ad.ReLU(V(xo)), 8 * 2 * R * (Cc + 1))
 timeit("sum rows ab->a", lambda: ad.Einsum("ab->a", V(x)), 8 * (n + R))
 timeit("sum cols ab->b", lambda: ad.Einsum("ab->b", V(x)), 8 * (n + Cc))
 timeit("sum all ab->", lambda: ad.Einsum("ab->", V(x)), 8 * n)
-timeit("softmax denominator bi,o->bo", lambda: ad.Einsum("bi,o->bo", V(x), np.array([1])), 8 * (n + R))
+one = ad.to_device(np.array([1.0]))     # (the reference passes the literal np.array([1]); resident here so the clock sees the kernel, not its upload)
+timeit("softmax denominator bi,o->bo", lambda: ad.Einsum("bi,o->bo", V(x), V(one)), 8 * (n + R))
 timeit("frobenius", lambda: ad.FrobeniusNorm(V(x)), 8 * n)
 lab = np.zeros((R, Cc)); lab[np.arange(R), rng.integers(0, Cc, R)] = 1.0
 labd = ad.to_device(lab)
 timeit("softmax_ce 8192x4096", lambda: ad.SoftmaxCEWithLogits(labels=V(labd), logits=V(x)), 8 * (2 * n + R))
+os.environ["ADB_SCE_RING"] = "0"
+timeit("softmax_ce 8192x4096 (register-resident kernel, ADB_SCE_RING=0)", lambda: ad.SoftmaxCEWithLogits(labels=V(labd), logits=V(x)), 8 * (2 * n + R))
+del os.environ["ADB_SCE_RING"]
+for cc in (512, 1024, 2048):
+    rr = n // cc
+    zz, ll = x.reshape_view((rr, cc)), labd.reshape_view((rr, cc))
+    timeit("softmax_ce %dx%d" % (rr, cc), lambda: ad.SoftmaxCEWithLogits(labels=V(ll), logits=V(zz)), 8 * (2 * n + rr))
+# the same reductions on a 1 GiB operand: separates the fixed ramp / tail cost of a 40 us kernel from its streaming rate
+xl = dev((4 * R, Cc))
+timeit("sum rows ab->a 1 GiB", lambda: ad.Einsum("ab->a", V(xl)), 8 * (4 * n + 4 * R))
+timeit("sum cols ab->b 1 GiB", lambda: ad.Einsum("ab->b", V(xl)), 8 * (4 * n + Cc))
+timeit("sum all ab-> 1 GiB", lambda: ad.Einsum("ab->", V(xl)), 8 * 4 * n)
+timeit("frobenius 1 GiB", lambda: ad.FrobeniusNorm(V(xl)), 8 * 4 * n)
+del xl
 p, g, m, v = dev((4097, 4096)), dev((4097, 4096)), dev((4097, 4096)), dev((4097, 4096), positive=True)
 
 
