@@ -79,59 +79,97 @@ def _freeze(v):
     return v
 
 
+_CLASS_KIND = {}         # class -> (is a Variable subclass, tapeable device op, attribute names)   [filled on first sight]
+_PLAIN_SIG = {}          # (class, number of children) -> the signature entry of an attribute-less op (one shared tuple)
+_ATOMS = (str, int, float, bool, type(None))
+
+
+def _class_kind(cls, is_device_node, probe):
+    attrs = _ATTRS.get(cls)
+    k = _CLASS_KIND[cls] = (issubclass(cls, Variable), attrs is not None and is_device_node(probe), attrs)
+    return k
+
+
 def scan(tops, scalar_of, has_value, is_device_node):
     """Pre-order walk of the sub-DAG that an evaluation of `tops` would touch.
-    Returns (order, leaves, signature) or None when the graph cannot be taped."""
+    Returns (order, leaves, signature) or None when the graph cannot be taped.
+    (This loop runs over every node of every evaluation - 44 k nodes for the second-order char-rnn - so the helpers
+    `has_value` / `scalar_of` / `is_device_node` of the engine are inlined for the common cases.)"""
     pos, order, leaves, sig = {}, [], [], []
     stack = list(reversed(tops))
-    attrs_of = _ATTRS
+    kinds, plain = _CLASS_KIND, _PLAIN_SIG
+    ndarray = np.ndarray
+    pop, push, get_pos = stack.pop, stack.extend, pos.get
+    add_sig, add_leaf, add_order = sig.append, leaves.append, order.append
     while stack:
-        n = stack.pop()
-        p = pos.get(id(n))
+        n = pop()
+        key = id(n)
+        p = get_pos(key)
         if p is not None:
-            sig.append(p)                        # sharing: a back-reference to an already visited node
+            add_sig(p)                           # sharing: a back-reference to an already visited node
             continue
-        pos[id(n)] = len(order)
-        order.append(n)
-        if isinstance(n, Variable) or has_value(n):
-            s = scalar_of(n)
-            if s is not None:
-                sig.append(("s", s))             # folded into programs as an immediate: the VALUE is structure
-                leaves.append(n)                 # (uploaded only if some kernel reads it as a tensor, see build_tape)
-                continue
-            if n._dev is not None:
-                d = n._dev
+        pos[key] = len(order)
+        add_order(n)
+        cls = type(n)
+        kind = kinds.get(cls)
+        if kind is None:
+            kind = _class_kind(cls, is_device_node, n)
+        if kind[0] or n._dev is not None or n._host is not None:
+            # ---- a leaf of this evaluation: a Variable, or a node that already has a value
+            if kind[0]:
+                if n._host is None and not n._dev_override and type(n._value) is ndarray:
+                    v = n._value
+                    s = float(v) if v.ndim == 0 else None           # == Variable.host_scalar() for the common case
+                else:
+                    s = n.host_scalar()
+                if s is not None:
+                    add_sig(("s", s))            # folded into programs as an immediate: the VALUE is structure
+                    add_leaf(n)                  # (uploaded only if some kernel reads it as a tensor, see build_tape)
+                    continue
+            d = n._dev
+            if d is not None:
                 if type(d) is not DeviceArray:
                     return None
-                sig.append(("d", d.shape, d.strides))
+                add_sig(("d", d.shape, d.strides))
             elif isinstance(n, ConstFill) and n.fill is not None and n._host is None:
-                sig.append(("c", n.fill, n._fill_shape))
+                add_sig(("c", n.fill, n._fill_shape))
             else:
                 v = n._host if n._host is not None else getattr(n, "_value", None)
                 if isinstance(v, DeviceArray):
-                    sig.append(("d", v.shape, v.strides))
-                elif isinstance(v, np.ndarray):
-                    sig.append(("h", v.shape))
+                    add_sig(("d", v.shape, v.strides))
+                elif isinstance(v, ndarray):
+                    add_sig(("h", v.shape))
                 else:
                     return None
-            leaves.append(n)
+            add_leaf(n)
             continue
-        leaves.append(None)
-        cls = type(n)
-        attrs = attrs_of.get(cls)
-        if attrs is None or not is_device_node(n) or "_eval_device" in n.__dict__:
+        add_leaf(None)
+        if not kind[1]:
             return None
+        nd = n.__dict__
+        if "_eval" in nd or "_eval_device" in nd:
+            return None                          # an instance-level override: not a pure function of (class, attributes)
+        attrs = kind[2]
+        children = n.children
         if attrs:
             key = []
             for a in attrs:
-                f = _freeze(getattr(n, a))
-                if f is None and getattr(n, a) is not None:
-                    return None
-                key.append(f)
-            sig.append((cls, len(n.children), tuple(key)))
+                v = getattr(n, a)
+                if type(v) not in _ATOMS:
+                    f = _freeze(v)
+                    if f is None and v is not None:
+                        return None
+                    v = f
+                key.append(v)
+            add_sig((cls, len(children), tuple(key)))
         else:
-            sig.append((cls, len(n.children)))
-        stack.extend(reversed(n.children))
+            ck = (cls, len(children))
+            e = plain.get(ck)
+            if e is None:
+                e = plain[ck] = ck
+            add_sig(e)
+        if children:
+            push(children[::-1])
     return order, leaves, tuple(sig)
 
 
@@ -171,7 +209,7 @@ class Tape:
 
 class _Graph:
     """One captured replay: the cudaGraphExec_t, the buffer its kernels address ([leaf staging | arena]) and its flags."""
-    __slots__ = ("exec", "buf", "refs", "stage_off", "arena_off", "flags", "nflags")
+    __slots__ = ("exec", "buf", "refs", "stage_off", "arena_off", "flags", "nflags", "last_stream")
 
     def __del__(self):
         ex = getattr(self, "exec", None)
@@ -352,6 +390,7 @@ def _capture(tape):
         stats["graph_rejected"] += 1
         return False
     g.exec = ex
+    g.last_stream = None
     g.refs = sys.getrefcount(g.buf)
     stats["graphs"] += 1
     return g
@@ -385,7 +424,11 @@ def _launch_graph(tape, g, order, bases, base_tensors, tops, add_pending_flag, o
         from . import engine
         if engine._pending_flags:
             engine.check_pending_flags()          # the flags of the previous launch are about to be re-zeroed
-    st = C.c_void_p(_device.stream_ptr())
+    sp = _device.stream_ptr()
+    st = C.c_void_p(sp)
+    if g.last_stream is not None and g.last_stream != sp:
+        check(L.adb_sync(C.c_void_p(g.last_stream)))      # the buffer is shared by all launches: never two in flight on two streams
+    g.last_stream = sp
     b0 = g.buf.data_ptr()
     for j, off in enumerate(g.stage_off):
         check(L.adb_memcpy_d2d(C.c_void_p(b0 + 8 * off), C.c_void_p(bases[j]), tape.ext_size[j], st))

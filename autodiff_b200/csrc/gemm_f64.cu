@@ -508,6 +508,20 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             if (s1 > total_kt / 16) s1 = total_kt / 16;
             if (s1 > 128) s1 = 128;
             if (s1 > 1) splits = (int)s1;
+            if (small && splits > 1) {
+                // 64x64 tiles, a few hundred CTAs: pick the split count by a cost model fitted to measurements
+                // (profiles/r01_gemm_small_splitk.log; unit = one k-tile step of one CTA that shares its SM, 0.52 us):
+                //   T(s) = [CTAs on the busiest SM] * [k-tiles per CTA] * (1.23 if the CTA is alone on its SM: one 64x64 CTA does
+                //          not saturate the DMMA pipe) + 12 (prologue + epilogue) + 15 if s > 1 (the partial-sum reduction launch).
+                // 512x1024x1024 (128 tiles): s = 1, 47 us instead of 51 with s = 2;  256x1024x1024 (64 tiles): s = 4, 31 us.
+                double best = 1e30;
+                for (long long sc = 1; sc <= s1; ++sc) {
+                    const long long per_sm = (tiles * sc + 147) / 148;
+                    const double kts = (double)((total_kt + sc - 1) / sc);
+                    const double t = (double)per_sm * kts * (per_sm >= 2 ? 1.0 : 1.23) + 12.0 + (sc > 1 ? 15.0 : 0.0);
+                    if (t < best - 1e-9) { best = t; splits = (int)sc; }
+                }
+            }
         }
         int kt_per_split = (total_kt + splits - 1) / splits;
         splits = (total_kt + kt_per_split - 1) / kt_per_split;

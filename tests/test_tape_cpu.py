@@ -79,3 +79,43 @@ def test_lookup_records_on_second_sighting_and_replays_after_store():
     tape.store(sig2, marker)
     assert tape.lookup(sig2) == (marker, False)
     tape.clear()
+
+
+def test_graph_replay_gating_without_a_gpu():
+    """When a tape may be replayed as one CUDA graph (tape._graph_for): only small-leaf tapes with enough calls and after
+    the first call-by-call replay; never while a value of the previous graph replay is still alive in the graph's buffer."""
+    import sys
+    import torch
+    from autodiff_b200.device import DeviceArray
+
+    class FakeBase:
+        def __init__(self, n):
+            self.n = n
+
+        def numel(self):
+            return self.n
+
+    t = tape.Tape()
+    t.ext_size, t.calls, t.replays, t.graph = [80], [None] * 10, 1, None
+    bases = [FakeBase(10)]
+    if not tape.GRAPH:
+        return
+    assert tape._graph_for(t, bases) is None and t.graph is None          # first replay: call by call
+    t.replays, t.calls = 5, [None] * (tape.GRAPH_MIN_CALLS - 1)
+    assert tape._graph_for(t, bases) is None and t.graph is None          # too few kernels to be worth a graph
+    t.calls, t.ext_size = [None] * 10, [tape.GRAPH_MAX_STAGE_BYTES + 8]
+    assert tape._graph_for(t, [FakeBase(tape.GRAPH_MAX_STAGE_BYTES // 8 + 1)]) is None and t.graph is None   # leaves too big to stage
+    t.ext_size = [80]
+    g = tape._Graph()
+    g.exec, g.buf = None, torch.zeros(8, dtype=torch.float64)
+    g.refs = sys.getrefcount(g.buf)
+    t.graph = g
+    assert tape._graph_for(t, bases) is g
+    assert tape._graph_for(t, [FakeBase(11)]) is None                     # a leaf is now a view of a differently sized array
+    busy = tape.stats["graph_busy"]
+    alive = DeviceArray._make(g.buf, 0, (2,), (1,))                        # what a node of the previous replay holds
+    assert tape._graph_for(t, bases) is None and tape.stats["graph_busy"] == busy + 1
+    del alive
+    assert tape._graph_for(t, bases) is g
+    t.graph = False                                                       # capture failed once: never tried again
+    assert tape._graph_for(t, bases) is None
