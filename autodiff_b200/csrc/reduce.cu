@@ -771,28 +771,28 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
         }
     }
     double m = -INFINITY;
-    bool has_nan = false;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { m = fmax(m, zq[k].v[e]); has_nan |= zq[k].v[e] != zq[k].v[e]; }
+        for (int e = 0; e < 4; ++e) m = fmax(m, zq[k].v[e]);
     }
     // the WARP's max first (plain fmax shuffles), so that each element costs exactly one exp
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    // fmax skips NaN, exp_nonpos does not: a NaN logit makes `se` NaN without a per-element test (np.max propagates NaN).
+    // A warp that holds nothing but -inf / padding subtracts 0 instead of its max (-inf - -inf would be NaN): se = 0.
+    const double mm = m == -INFINITY ? 0.0 : m;
     double se = 0.0, lsum = 0.0, dot = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
-            se += exp_nonpos(zq[k].v[e] - m);          // straight-line (no branch per element): the 4K evaluations interleave.
-            dot += c < cols ? lq[k].v[e] * zq[k].v[e] : 0.0;   // Padding is -inf -> 0; a warp of only -inf (m = -inf) yields NaN
-            lsum += lq[k].v[e];                        // here and is discarded by the M == -inf test of the combine below
+            se += exp_nonpos(zq[k].v[e] - mm);         // straight-line (no branch per element): the 4K evaluations interleave;
+            dot += c < cols ? lq[k].v[e] * zq[k].v[e] : 0.0;   // padding is -inf -> exp = 0
+            lsum += lq[k].v[e];
         }
     }
-    if (m == -INFINITY) se = 0.0;              // nothing but -inf (or padding) in this warp: contributes no mass
-    if (has_nan) se = NAN;                     // np.max propagates NaN (fmax does not)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         se += __shfl_xor_sync(0xffffffffu, se, off);

@@ -121,16 +121,16 @@ softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const 
             arm(k + SPG);
         }
         double m = -INFINITY;
-        bool has_nan = false;
 #pragma unroll
-        for (int e = 0; e < 2 * P; ++e) { m = fmax(m, z[e]); has_nan |= z[e] != z[e]; }
+        for (int e = 0; e < 2 * P; ++e) m = fmax(m, z[e]);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        // fmax skips NaN, exp_nonpos does not: a NaN logit makes `se` NaN without a per-element test (np.max propagates NaN).
+        // A warp that holds nothing but -inf / padding subtracts 0 instead of its max (-inf - -inf would be NaN): se = 0.
+        const double mm = m == -INFINITY ? 0.0 : m;
         double se = 0.0;
 #pragma unroll
-        for (int e = 0; e < 2 * P; ++e) se += exp_nonpos(z[e] - m);   // straight-line: the 2P evaluations interleave; padding: exp(-inf) = 0
-        if (m == -INFINITY) se = 0.0;                  // nothing but -inf (or padding) in this warp: (-inf) - (-inf) gave NaN above
-        if (has_nan) se = NAN;                         // np.max propagates NaN (fmax does not)
+        for (int e = 0; e < 2 * P; ++e) se += exp_nonpos(z[e] - mm);  // straight-line: the 2P evaluations interleave; padding: exp(-inf) = 0
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             se += __shfl_xor_sync(0xffffffffu, se, off);
