@@ -51,12 +51,13 @@ GRAPH = os.environ.get("ADB_TAPE_GRAPH", "1") != "0"
 GRAPH_AFTER_REPLAYS = int(os.environ.get("ADB_TAPE_GRAPH_AFTER", "1"))   # call-by-call replays before a tape is captured (0 with
 GRAPH_MIN_CALLS = int(os.environ.get("ADB_TAPE_GRAPH_MIN_CALLS", "4"))   # ADB_TAPE_SELFCHECK=1: every graph of the test-suite)
 GRAPH_MAX_STAGE_BYTES = 64 << 20       # leaves are copied next to the arena on every replay: only worth it when they are small
+GRAPH_MAX_TOTAL_BYTES = int(os.environ.get("ADB_TAPE_GRAPH_BYTES", str(64 << 30)))   # all graph buffers together (they outlive the step)
 SCE_ERROR = "Labels must be a valid probability distribution!"
 
 _seen = {}               # signature -> sightings so far
 _tapes = {}              # signature -> Tape | False (not tapeable)
 _recorder = None         # active Recorder (set while a recording evaluation runs)
-stats = {"replays": 0, "records": 0, "rejected": 0, "graphs": 0, "graph_launches": 0, "graph_rejected": 0, "graph_busy": 0}
+stats = {"replays": 0, "records": 0, "rejected": 0, "graphs": 0, "graph_launches": 0, "graph_rejected": 0, "graph_busy": 0, "graph_bytes": 0}
 _cap_stream = None       # side stream the graphs are captured on (the legacy default stream cannot be captured)
 
 # node classes whose device evaluation is a pure function of (class, these attributes, children): filled by register()
@@ -212,6 +213,9 @@ class _Graph:
     __slots__ = ("exec", "buf", "refs", "stage_off", "arena_off", "flags", "nflags", "last_stream")
 
     def __del__(self):
+        buf = getattr(self, "buf", None)
+        if buf is not None:
+            stats["graph_bytes"] -= buf.numel() * 8
         ex = getattr(self, "exec", None)
         if ex:
             try:
@@ -347,7 +351,13 @@ def _capture(tape):
         g.stage_off.append(total)
         total += (sz // 8 + 31) // 32 * 32
     g.arena_off = total
+    g.buf = None
+    nbytes = 8 * (total + max(tape.arena_elems, 2))
+    if stats["graph_bytes"] + nbytes > GRAPH_MAX_TOTAL_BYTES:
+        stats["graph_rejected"] += 1              # the buffers of captured tapes stay allocated: bounded in total
+        return False
     g.buf = t.empty(total + max(tape.arena_elems, 2), dtype=t.float64, device="cuda")
+    stats["graph_bytes"] += nbytes
     g.nflags = sum(1 for c in tape.calls if c.flag_arg >= 0)
     g.flags = t.zeros(max(g.nflags, 1), dtype=t.int32, device="cuda")
     if _cap_stream is None:
