@@ -15,7 +15,7 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 ad.init(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-sizes, gb, steps = [40, 64, 32, 10], 96, 6
+sizes, gb, steps = [40, 64, 32, 10], 96, 8
 rng = np.random.default_rng(7)
 xs = [rng.standard_normal((gb, sizes[0])) for _ in range(steps)]
 ys = [np.eye(sizes[-1])[rng.integers(0, sizes[-1], gb)] for _ in range(steps)]
