@@ -101,6 +101,21 @@ class Optimizer(Module):
     def _stepped(self):
         pass
 
+    def update_one(self, k, param, grad):
+        """The update of parameter k alone (same arithmetic as one iteration of `_forward`): lets a training loop queue
+        each parameter's update as soon as its gradient exists (autodiff_b200.dp overlaps it with the rest of the backward
+        pass).  Call `end_step()` once after the last parameter of a step."""
+        slots = [getattr(self, name) for name in self.STATE]
+        out = self.fn(*self._leading(), *[slot[k] for slot in slots], param, grad)
+        if not self.STATE:
+            return out
+        for slot, value in zip(slots, out[1:]):
+            slot[k] = value
+        return out[0]
+
+    def end_step(self):
+        self._stepped()
+
     def _forward(self, params_list, grads_list):
         if not isinstance(params_list, list):
             params_list = list(params_list)

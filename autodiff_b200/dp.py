@@ -9,6 +9,7 @@ the GLOBAL batch, as examples/feedforward_mnist.py:25 divides by a constant).  T
 launched as soon as its dW kernel is queued and overlaps the remaining backward GEMMs; the optimizer runs
 replicated (identical inputs => identical weights, no broadcast after step 0).
 """
+import math
 import os
 import time
 
@@ -17,7 +18,7 @@ import numpy as np
 from .core.engine import check_pending_flags, evaluate_many
 from .core.grad import grad
 from .core.high_level_ops import NN, Adam
-from .core.node import Variable
+from .core.node import Node, Variable
 from .core.ops import Einsum, SoftmaxCEWithLogits
 from .device import DeviceArray, pinned_empty, synchronize, to_device, to_host, torch
 
@@ -47,8 +48,22 @@ def allreduce_async(dev_array, dist):
     return dist.all_reduce(_flat_view(dev_array), op=dist.ReduceOp.SUM, async_op=True)
 
 
-def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True):
-    """One step of examples/feedforward_mnist.py:17-34 on this rank's shard.  x, y: host ndarrays or DeviceArrays."""
+_opt_stream = None
+
+
+def _optimizer_stream():
+    global _opt_stream
+    if _opt_stream is None:
+        _opt_stream = torch().cuda.Stream()
+    return _opt_stream
+
+
+def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_optimizer=True):
+    """One step of examples/feedforward_mnist.py:17-34 on this rank's shard.  x, y: host ndarrays or DeviceArrays.
+    With `overlap_optimizer` (and an optimizer that has `update_one`) the update of each parameter is queued on a side
+    stream as soon as its gradient is reduced, so the HBM-bound Adam kernels of layer L run under the DMMA-bound backward
+    GEMMs of the layers below it instead of after them (same kernels, same operands: bit-identical results)."""
+    from . import _lib, device as _device
     xv = Variable(x, name="images")
     yv = Variable(y, name="labels")
     logits = nn(xv)
@@ -56,9 +71,21 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True):
     cost = Einsum("i->", sce) / global_batch
     grads = grad(cost, nn.w)
     works = []
+    # (worth two stream switches per parameter only when the update kernels are not tiny: >= 1 M elements somewhere)
+    overlap = (overlap_optimizer and hasattr(opt, "update_one") and max(math.prod(w.shape) for w in nn.w) >= (1 << 20)
+               and all(isinstance(g, Node) for g in grads))
+    new_w = [None] * len(grads)
+    if overlap:
+        index_of = {id(g): k for k, g in enumerate(grads)}
+        t = torch()
+        main = t.cuda.current_stream()
+        side = _optimizer_stream()
 
     def ready(node):                               # fires when a gradient's kernels are queued
-        if dist is not None and node is not cost:
+        if node is cost:
+            return
+        work = None
+        if dist is not None:
             d = node._dev
             if d.size <= 16 or any(st == 0 and dim > 1 for dim, st in zip(d.shape, d.strides)):
                 # a gradient that ALIASES a shared constant (broadcast ones, a cached tiny upload) must not be reduced
@@ -67,23 +94,78 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True):
                 own = DeviceArray.empty(d.shape)
                 copy_device(d, own)
                 node._dev = d = own
-            works.append(allreduce_async(d, dist))
+            work = allreduce_async(d, dist)
+        k = index_of.get(id(node)) if overlap else None
+        if k is None or new_w[k] is not None:
+            if work is not None:
+                works.append(work)
+            return
+        # the update of parameter k on the side stream: behind the gradient's kernels (and its all-reduce), beside
+        # everything the main stream queues from here on.  A recording launch tape must not log these calls.
+        done = t.cuda.Event()
+        done.record(main)
+        saved = (_lib._call_hook, _device._alloc_hook)
+        _lib._call_hook = None
+        _device._alloc_hook = lambda base: base.record_stream(main)      # the new weights / moments are read on `main` next step
+        try:
+            with t.cuda.stream(side):
+                side.wait_event(done)
+                if work is not None:
+                    work.wait()
+                _device.use_stream(side)
+                new_w[k] = opt.update_one(k, nn.w[k], node._dev)
+        finally:
+            _device.use_stream(main)
+            _lib._call_hook, _device._alloc_hook = saved
     # one fusion plan (and one launch tape) over all outputs; last layer's dW is needed first, so it is evaluated
     # first and its all-reduce overlaps the rest of the backward pass
     evaluate_many(list(reversed(grads)) + ([cost] if read_loss else []), on_ready=ready)
-    gdev = [g.eval_device() for g in grads]
     for w in works:
         w.wait()
-    new_w = opt(list(nn.w), gdev)
+    if overlap:
+        main.wait_stream(side)
+        for k, g in enumerate(grads):              # (a gradient whose callback never fired: update it here)
+            if new_w[k] is None:
+                new_w[k] = opt.update_one(k, nn.w[k], g.eval_device())
+        opt.end_step()
+    else:
+        new_w = opt(list(nn.w), [g.eval_device() for g in grads])
     opt.apply_new_weights(nn.w, new_w)
     loss = None
     if read_loss:
         lv = cost.eval_device()
         if dist is not None:
             dist.all_reduce(_flat_view(lv), op=dist.ReduceOp.SUM)
+        if read_loss == "deferred":
+            return PendingLoss(lv)
         loss = float(to_host(lv))
         check_pending_flags()                      # deferred label validation of SoftmaxCEWithLogits (reference ops.py:246-248)
     return loss
+
+
+class PendingLoss:
+    """The loss of a step whose device->host copy is queued but not waited for (`train_step(..., read_loss="deferred")`).
+    A loop that reads step k's loss after queueing step k+1 lets Python build the next graph while the GPU still runs
+    (4.7 ms of host work per configs[2] step: graph build, ad.grad, tape replay - measured to be hidden already at >= 1024
+    rows per rank, `profiles/r01_shard_step_probe_v2.log`, so bench.py reads synchronously); `value()` blocks until the copy
+    is done and raises the deferred label-validation error of SoftmaxCEWithLogits, like the synchronous path."""
+
+    def __init__(self, loss_dev):
+        from . import _lib
+        from .device import copy_device, stream_ptr
+        import ctypes as C
+        t = torch()
+        self._own = DeviceArray.empty(())             # (not a view of the step's arena: holding one would pin a graph's buffer)
+        copy_device(loss_dev, self._own)
+        self._host = pinned_empty((1,))
+        _lib.check(_lib.lib().adb_memcpy_d2h(C.c_void_p(self._host.ctypes.data), C.c_void_p(self._own.ptr), 8, C.c_void_p(stream_ptr())))
+        self._done = t.cuda.Event()
+        self._done.record(t.cuda.current_stream())
+
+    def value(self):
+        self._done.synchronize()
+        check_pending_flags()
+        return float(self._host[0])
 
 
 def _mlp_flops(sizes, batch):
@@ -151,11 +233,16 @@ def bench_mlp(args, dist):
     xd, yd = to_device(x), to_device(y)
     del x, y
     steps = max(2, min(args.steps, 5))
-    ms = timed(lambda: train_step(nn, opt, xd, yd, gbatch, dist, read_loss=True), steps, 4)     # (tape: recorded on step 2, first replay on step 3)
+    last = {}
+
+    def c3_step():
+        last["loss"] = train_step(nn, opt, xd, yd, gbatch, dist, read_loss=True)
+    ms = timed(c3_step, steps, 4)     # (tape: recorded on step 2, first replay on step 3)
     fl = _mlp_flops(sizes, gbatch)
     out["c3_mlp_4096x8_b8192"] = {"samples_per_s": round(gbatch / (ms * 1e-3), 1), "ms_per_step": round(ms, 3), "n_gpus": ws,
                                   "global_batch": gbatch, "scaling": "strong", "gemm_tflops": round(fl / (ms * 1e-3) / 1e12, 2),
                                   "allreduce_bytes_per_step": sum((a + 1) * b * 8 for a, b in zip(sizes, sizes[1:])),
-                                  "includes": "graph build + ad.grad + kernels + per-layer NCCL all-reduce overlapped with backward + "
-                                              "Adam on device + all-reduced loss read back to the host; inputs resident in HBM"}
+                                  "loss": last.get("loss"),
+                                  "includes": "graph build + ad.grad + kernels + per-layer NCCL all-reduce and per-layer Adam (side stream) overlapped "
+                                              "with backward + all-reduced loss read back to the host every step; inputs resident in HBM"}
     return out

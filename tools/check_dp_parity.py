@@ -16,6 +16,8 @@ ad.init(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sizes, gb, steps = [40, 64, 32, 10], 96, 8
+if "big" in sys.argv[1:]:      # a parameter of >= 1 M elements: dp.train_step queues each layer's optimizer update on a side stream
+    sizes = [1100, 1024, 10]
 rng = np.random.default_rng(7)
 xs = [rng.standard_normal((gb, sizes[0])) for _ in range(steps)]
 ys = [np.eye(sizes[-1])[rng.integers(0, sizes[-1], gb)] for _ in range(steps)]
@@ -25,8 +27,12 @@ nn = ad.NN(sizes)
 opt = ad.Adam(len(nn.w), lr=1e-2)
 lo, hi = dp.shard_rows(gb, world, rank)
 losses = []
-for s in range(steps):
-    losses.append(dp.train_step(nn, opt, xs[s][lo:hi], ys[s][lo:hi], gb, dist if world > 1 else None, read_loss=True))
+if "deferred" in sys.argv[1:]:  # every loss read one step late (dp.PendingLoss): the host builds step k+1 while the GPU runs step k
+    pending = [dp.train_step(nn, opt, xs[s][lo:hi], ys[s][lo:hi], gb, dist if world > 1 else None, read_loss="deferred") for s in range(steps)]
+    losses = [p.value() for p in pending]
+else:
+    for s in range(steps):
+        losses.append(dp.train_step(nn, opt, xs[s][lo:hi], ys[s][lo:hi], gb, dist if world > 1 else None, read_loss=True))
 w_gpu = [np.asarray(w.value if not isinstance(w.value, ad.DeviceArray) else ad.to_host(w.value)) for w in nn.w]
 
 if rank == 0:
@@ -44,7 +50,7 @@ if rank == 0:
     err_l = max(abs(a - b) / abs(b) for a, b in zip(losses, rlosses))
     err_w = max(float(np.max(np.abs(a - np.asarray(b.value))) / np.max(np.abs(np.asarray(b.value)))) for a, b in zip(w_gpu, rnn.w))
     from autodiff_b200.core import tape
-    print({"world": world, "steps": steps, "loss_rel_err": err_l, "weight_rel_err": err_w, "tape": dict(tape.stats), "ok": bool(err_l < 1e-12 and err_w < 1e-12)})
+    print({"world": world, "sizes": sizes, "steps": steps, "args": sys.argv[1:], "loss_rel_err": err_l, "weight_rel_err": err_w, "tape": dict(tape.stats), "ok": bool(err_l < 1e-12 and err_w < 1e-12)})
     assert err_l < 1e-12 and err_w < 1e-12
 if world > 1:
     dist.destroy_process_group()
