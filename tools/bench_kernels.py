@@ -166,6 +166,13 @@ timeit("C2c fwd ijkl,jl->ik", lambda: ad.Einsum("ijkl,jl->ik", V(A4), V(B2)), nb
 timeit("C2c dB ijkl,ik->jl", lambda: ad.Einsum("ijkl,ik->jl", V(A4), V(G2)), nb)
 timeit("C2c dA ik,jl->ijkl", lambda: ad.Einsum("ik,jl->ijkl", V(G2), V(B2)), nb)
 del A4
+S = 64                                        # SURVEY 8d asks for the 64^4 member too: 128 MiB, 20 us of traffic - ramp/tail-bound
+A4 = dev((S, S, S, S)); B2 = dev((S, S)); G2 = dev((S, S))
+nb = 8 * (S ** 4 + 2 * S * S)
+timeit("C2c 64^4 fwd ijkl,jl->ik", lambda: ad.Einsum("ijkl,jl->ik", V(A4), V(B2)), nb)
+timeit("C2c 64^4 dB ijkl,ik->jl", lambda: ad.Einsum("ijkl,ik->jl", V(A4), V(G2)), nb)
+timeit("C2c 64^4 dA ik,jl->ijkl", lambda: ad.Einsum("ik,jl->ijkl", V(G2), V(B2)), nb)
+del A4
 for (M, N, K, tag) in ((8192, 8192, 8192, "C2a"), (8192, 4096, 4097, "C3 fwd"), (1024, 4096, 4097, "C3 fwd b/8"), (512, 1024, 1024, "C5 h@w")):
     a, bb = dev((M, K)), dev((K, N))
     timeit("gemm %s %dx%dx%d" % (tag, M, N, K), lambda: V(a) @ V(bb), 8 * (M * K + K * N + M * N), flops=2.0 * M * N * K, reps=4)
