@@ -80,14 +80,14 @@ def _freeze(v):
     return v
 
 
-_CLASS_KIND = {}         # class -> (is a Variable subclass, tapeable device op, attribute names)   [filled on first sight]
+_CLASS_KIND = {}         # class -> (is a Variable subclass, tapeable device op, attribute names, is exactly Variable)   [filled on first sight]
 _PLAIN_SIG = {}          # (class, number of children) -> the signature entry of an attribute-less op (one shared tuple)
 _ATOMS = (str, int, float, bool, type(None))
 
 
 def _class_kind(cls, is_device_node, probe):
     attrs = _ATTRS.get(cls)
-    k = _CLASS_KIND[cls] = (issubclass(cls, Variable), attrs is not None and is_device_node(probe), attrs)
+    k = _CLASS_KIND[cls] = (issubclass(cls, Variable), attrs is not None and is_device_node(probe), attrs, cls is Variable)
     return k
 
 
@@ -118,11 +118,11 @@ def scan(tops, scalar_of, has_value, is_device_node):
         if kind[0] or n._dev is not None or n._host is not None:
             # ---- a leaf of this evaluation: a Variable, or a node that already has a value
             if kind[0]:
-                if n._host is None and not n._dev_override and type(n._value) is ndarray:
+                if kind[3] and n._host is None and not n._dev_override and type(n._value) is ndarray:
                     v = n._value
                     s = float(v) if v.ndim == 0 else None           # == Variable.host_scalar() for the common case
                 else:
-                    s = n.host_scalar()
+                    s = n.host_scalar()                             # (subclasses: ConstFill._value would MATERIALISE the constant)
                 if s is not None:
                     add_sig(("s", s))            # folded into programs as an immediate: the VALUE is structure
                     add_leaf(n)                  # (uploaded only if some kernel reads it as a tensor, see build_tape)
