@@ -198,6 +198,10 @@ struct Red3Params {
     double* out;
     double* partial;      // [splits][NG * fin_vec]
     int* counter;         // one arrival counter per blockIdx.x (self-resetting); the last slice to arrive adds the partials
+    // row kernels: an operand that does not depend on the summed indices ('bi,o->bo': the Softmax denominator's [1];
+    // 'ab,a->a') is factored out of the sum and multiplied in once per output - one load per output instead of one per step
+    const double* post;
+    long long post_os[3];
 };
 
 // Arrival of this CTA's slice: returns true in every thread of the LAST slice to arrive for blockIdx.x, after which
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
     const unsigned hi = (lo + P.chunk < P.R) ? lo + P.chunk : P.R;
 
     unsigned rem = live ? o : 0;
-    long long out_off = 0;
+    long long out_off = 0, post_off = 0;
     const double* base[NOPS];
 #pragma unroll
     for (int t = 0; t < NOPS; ++t) base[t] = P.op[t];
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
         const unsigned i = rem - qn * P.odiv[k].d;
         rem = qn;
         out_off += (long long)i * P.out_s[k];
+        post_off += (long long)i * P.post_os[k];
 #pragma unroll
         for (int t = 0; t < NOPS; ++t) base[t] += (long long)i * P.op_os[t][k];
     }
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
         }
     }
     if (P.splits == 1) {
-        if (lane == 0 && live) P.out[out_off] = a;
+        if (lane == 0 && live) P.out[out_off] = P.post ? a * __ldg(P.post + post_off) : a;
         return;
     }
     if (lane == 0 && live) P.partial[(long long)z * P.NG + o] = a;
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
             for (int w = 0; w < 8; ++w) t += warp_fin[w];
         }
     }
-    if (lane == 0) P.out[out_off] = t;
+    if (lane == 0) P.out[out_off] = P.post ? t * __ldg(P.post + post_off) : t;
 }
 
 template <int WR, int NOPS, int VEC>
@@ -515,13 +520,24 @@ static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
 
     Red3Params P;
     memset(&P, 0, sizeof P);
-    P.n_ops = S.n_ops; P.square = S.square;
+    P.square = S.square;
+    int nt = 0;
     for (int t = 0; t < S.n_ops; ++t) {
-        P.op[t] = S.op[t];
-        P.op_r0s[t] = S.op_rs[t][0];
-        P.op_r1s[t] = S.n_r > 1 ? S.op_rs[t][1] : 0;
-        for (int k = 0; k < 3; ++k) P.op_os[t][k] = k < S.n_o ? S.op_os[t][k] : 0;
+        const long long r0s = S.op_rs[t][0], r1s = S.n_r > 1 ? S.op_rs[t][1] : 0;
+        if (row && !P.post && r0s == 0 && r1s == 0 && S.n_ops - t + nt > 1 && !S.square) {
+            // independent of the summed indices: sum_r x[o,r] * s[o] = s[o] * sum_r x[o,r]  (1 ulp-level re-association)
+            P.post = S.op[t];
+            for (int k = 0; k < 3; ++k) P.post_os[k] = k < S.n_o ? S.op_os[t][k] : 0;
+            continue;
+        }
+        P.op[nt] = S.op[t];
+        P.op_r0s[nt] = r0s;
+        P.op_r1s[nt] = r1s;
+        for (int k = 0; k < 3; ++k) P.op_os[nt][k] = k < S.n_o ? S.op_os[t][k] : 0;
+        ++nt;
     }
+    P.n_ops = nt;
+    const int n_ops = nt;
     for (int k = 0; k < 3; ++k) P.out_s[k] = k < S.n_o ? S.out_s[k] : 0;
     P.out = S.out;
     P.O0 = (unsigned)O0;
@@ -529,7 +545,7 @@ static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
     // 256-bit path: every operand is unit-stride or broadcast along the vector dimension, and quad-aligned elsewhere
     int vec = 4;
     unsigned vecmask = 0;
-    for (int t = 0; t < S.n_ops && vec == 4; ++t) {
+    for (int t = 0; t < n_ops && vec == 4; ++t) {
         const long long vs = row ? P.op_r0s[t] : P.op_os[t][0];
         if (vs == 0) continue;
         if (vs != 1 || !aligned32(P.op[t])) { vec = 1; break; }

@@ -505,6 +505,9 @@ REDUCTIONS = [
     ("ijkl,jl->ik", [(9, 11, 13, 15), (11, 15)]), ("ijkl,ik->jl", [(9, 11, 13, 15), (9, 13)]),
     ("bi,o->bo", [(257, 1000), (1,)]), ("ab,ab->a", [(130, 2048), (130, 2048)]), ("ab,ab->b", [(2048, 132), (2048, 132)]),
     ("ab,b->a", [(300, 1024), (1024,)]), ("ab,a->b", [(1024, 300), (1024,)]), ("ab,bc,c->a", [(40, 300), (300, 9), (9,)]),
+    # an operand that does not depend on the summed index is factored out of the row reduction (one load per output)
+    ("ab,a->a", [(300, 1024), (300,)]), ("bi,o->bo", [(700, 4096), (1,)]), ("abc,a,c->a", [(9, 40, 128), (9,), (128,)]),
+    ("abc,ab->ab", [(12, 33, 512), (12, 33)]),
 ]
 
 
