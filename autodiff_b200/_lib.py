@@ -63,6 +63,7 @@ PROTOTYPES = {
     "adb_einsum_describe": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.c_char_p, C.c_size_t]),
     "adb_reduce_sum": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "adb_sum_squares": (C.c_int, [C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
+    "adb_norm2": (C.c_int, [C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "adb_softmax_ce": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "adb_im2col": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
     "adb_col2im": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),

@@ -533,6 +533,12 @@ class FrobeniusNorm(Node):
     def _eval_device(self):
         # reference ops.py:369: sqrt(sum([np.sum(np.square(x)) for x in nodes])) — one reduction per node, then
         # one tiny program adds the partials left to right and takes the root.
+        if len(self.nodes) == 1:            # one tensor: the root is taken inside the reduction's last slice (one launch)
+            x = dev(self.nodes[0])
+            out = DeviceArray.empty(())
+            tx = x.tensor()
+            _lib.call("adb_norm2", C.byref(tx), C.c_void_p(out.ptr), C.c_void_p(stream_ptr()))
+            return out
         parts = []
         for n in self.nodes:
             x = dev(n)

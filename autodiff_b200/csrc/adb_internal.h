@@ -15,6 +15,7 @@ int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor*
               cudaStream_t st);
 struct ReduceSpec {           // dims innermost-first, already collapsed (see reduce.cu)
     int n_ops, n_o, n_r, group, square;
+    int post_sqrt;            // single scalar output only: store sqrt(sum) (FrobeniusNorm of one tensor, reference ops.py:369)
     long long odim[4], rdim[4], out_s[4];
     long long op_os[ADB_RED_MAX_OPS][4], op_rs[ADB_RED_MAX_OPS][4];
     const double* op[ADB_RED_MAX_OPS];

@@ -365,12 +365,13 @@ int adb_reduce_sum(const adb_tensor* x, const adb_tensor* out, void* stream) {
     return adb::run_problem(P, reinterpret_cast<cudaStream_t>(stream), nullptr);
 }
 
-// np.sum(np.square(x)) — reference ops.py:369 (FrobeniusNorm).
-int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* stream) {
+// np.sum(np.square(x)) — reference ops.py:369 (FrobeniusNorm); take_root: sqrt of it in the same launch.
+static int sum_squares_impl(const adb_tensor* x, double* out_scalar, void* stream, int take_root) {
     adb::ReduceSpec S;
     memset(&S, 0, sizeof S);
     S.n_ops = 1;
     S.square = 1;
+    S.post_sqrt = take_root;
     S.op[0] = x->ptr;
     S.out = out_scalar;
     // order dims by |stride| ascending and collapse
@@ -396,6 +397,11 @@ int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* stream) {
     S.n_o = 0;
     S.group = (n > 0 && S.rdim[0] >= 64) ? 32 : (n > 0 && S.rdim[0] >= 8 ? 8 : 1);
     return adb::reduce_run(S, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" {
+int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* stream) { return sum_squares_impl(x, out_scalar, stream, 0); }
+int adb_norm2(const adb_tensor* x, double* out_scalar, void* stream) { return sum_squares_impl(x, out_scalar, stream, 1); }
 }
 
 }  // extern "C"

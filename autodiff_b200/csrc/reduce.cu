@@ -202,6 +202,7 @@ struct Red3Params {
     // 'ab,a->a') is factored out of the sum and multiplied in once per output - one load per output instead of one per step
     const double* post;
     long long post_os[3];
+    int post_sqrt;        // row kernels, one output: store sqrt(sum)
 };
 
 // Arrival of this CTA's slice: returns true in every thread of the LAST slice to arrive for blockIdx.x, after which
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
         }
     }
     if (P.splits == 1) {
-        if (lane == 0 && live) P.out[out_off] = P.post ? a * __ldg(P.post + post_off) : a;
+        if (lane == 0 && live) P.out[out_off] = P.post ? a * __ldg(P.post + post_off) : (P.post_sqrt ? sqrt(a) : a);
         return;
     }
     if (lane == 0 && live) P.partial[(long long)z * P.NG + o] = a;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
             for (int w = 0; w < 8; ++w) t += warp_fin[w];
         }
     }
-    if (lane == 0) P.out[out_off] = P.post ? t * __ldg(P.post + post_off) : t;
+    if (lane == 0) P.out[out_off] = P.post ? t * __ldg(P.post + post_off) : (P.post_sqrt ? sqrt(t) : t);
 }
 
 template <int WR, int NOPS, int VEC>
@@ -515,12 +516,14 @@ static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
     if (O <= 0) return 0;
     if (O >= (1LL << 31) || R >= (1LL << 31) || R <= 0) return -1;
     const bool row = S.group > 1;
+    if (S.post_sqrt && (!row || O != 1)) return -1;   // (the generic path below takes the root in a second launch)
     if (row && R < 128) return -1;                    // short rows, many outputs: the sub-warp groups of reduce_kernel fit better
     const long long R0 = S.rdim[0], O0 = S.n_o > 0 ? S.odim[0] : 1;
 
     Red3Params P;
     memset(&P, 0, sizeof P);
     P.square = S.square;
+    P.post_sqrt = S.post_sqrt;
     int nt = 0;
     for (int t = 0; t < S.n_ops; ++t) {
         const long long r0s = S.op_rs[t][0], r1s = S.n_r > 1 ? S.op_rs[t][1] : 0;
@@ -623,6 +626,8 @@ static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
     return 0;
 }
 
+__global__ void sqrt_scalar_kernel(double* p) { *p = sqrt(*p); }
+
 template <int G>
 static void launch_reduce(const RedParams& P, dim3 grid, cudaStream_t st) {
     switch (P.n_ops) {
@@ -704,6 +709,12 @@ int reduce_run(const ReduceSpec& S, cudaStream_t st) {
         if (e != cudaSuccess) return set_error("reduce finalize launch failed: %s", cudaGetErrorString(e));
         count_launch();
         cudaFreeAsync(P.partial, st);
+    }
+    if (S.post_sqrt) {
+        sqrt_scalar_kernel<<<1, 1, 0, st>>>(S.out);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error("reduce sqrt launch failed: %s", cudaGetErrorString(e));
+        count_launch();
     }
     return 0;
 }

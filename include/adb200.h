@@ -145,6 +145,9 @@ ADB_API int adb_einsum_describe(const char* op_str, int n_ops, const adb_tensor*
  *      as single-operand einsums.  out has x's rank with size-1 dims on the reduced axes. */
 ADB_API int adb_reduce_sum(const adb_tensor* x, const adb_tensor* out, void* stream);
 ADB_API int adb_sum_squares(const adb_tensor* x, double* out_scalar, void* stream);
+/* sqrt(np.sum(np.square(x))): FrobeniusNorm of ONE tensor (ops.py:369 with a single node) in one launch - the root is taken by
+ * the last slice of the reduction. */
+ADB_API int adb_norm2(const adb_tensor* x, double* out_scalar, void* stream);
 
 /* ---- SoftmaxCEWithLogits._eval, reference ops.py:243-255.  labels/logits: (rows, cols) views;
  *      out: rows elements (stride out_stride).  *flag (device int) is OR-ed with 1 when a label row does

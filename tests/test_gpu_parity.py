@@ -541,6 +541,15 @@ def test_frobenius_norm_large(ad):
     xs = [rng.standard_normal((1031, 517)), rng.standard_normal((4097, 64)), rng.standard_normal(11)]
     got = ad.FrobeniusNorm(*[ad.Variable(x, name="x%d" % i) for i, x in enumerate(xs)])()
     check(got, np.sqrt(sum(np.sum(np.square(x)) for x in xs)))
+    # one tensor: adb_norm2 takes the root inside the reduction (row kernel, sliced row kernel, generic fallbacks, views)
+    for x in xs + [rng.standard_normal((2048, 2048)), rng.standard_normal(7), rng.standard_normal((3, 5, 70)), rng.standard_normal((40, 300))[:, 1:-1]]:
+        got = ad.FrobeniusNorm(ad.Variable(x, name="x"))()
+        assert np.shape(got) == ()
+        check(got, np.sqrt(np.sum(np.square(x))))
+        g = ad.grad(ad.FrobeniusNorm(ad.Variable(x, name="x")) * 2.0, [ad.Variable(x)])    # (unrelated variable: zero gradient path still builds)
+    X = ad.Variable(xs[0], name="x")
+    dn = ad.grad(ad.FrobeniusNorm(X), [X])[0]()
+    check(dn, xs[0] / np.sqrt(np.sum(np.square(xs[0]))))
 
 
 def test_eval_many_pipelined_matches_sequential(ad):
