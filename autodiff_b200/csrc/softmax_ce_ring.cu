@@ -58,17 +58,21 @@ __device__ __forceinline__ void group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory");
 }
 
-// GT threads per group, P = 16-byte pairs per thread: columns <= GT * 2 * P.  GROUPS * SPG slots of 2 * row_bytes each.
-template <int P, int GROUPS, int SPG, int GT>
+// GT threads per group, P = 16-byte pairs per thread.  HALVES = 1: a slot holds a whole row (columns <= GT * 2 * P).
+// HALVES = 2 (4096 < columns <= 8192): a row travels as two half-rows through the same slot, first GT * 2 * P columns, then
+// the rest; the group keeps a running (max, sum exp) per warp across the halves - online log-sum-exp, one extra exp per
+// lane and half - and exchanges / finalises once per row.  GROUPS * SPG slots of 2 * half_bytes each.
+template <int P, int GROUPS, int SPG, int GT, int HALVES>
 __global__ void __launch_bounds__(GROUPS * GT, 1)
 softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits, long long z_sr,
-                       double* __restrict__ out, long long o_s, long long rows, unsigned cols, unsigned row_bytes,
+                       double* __restrict__ out, long long o_s, long long rows, unsigned cols, unsigned half_bytes,
                        int* __restrict__ flag) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) unsigned long long bars[GROUPS * SPG];
     constexpr int NW = GT / 32;
+    constexpr unsigned HALF_COLS = GT * 2 * P;         // columns of the first half when HALVES == 2
     __shared__ double xch[GROUPS][2][4][NW];           // [group][row parity][quantity][warp]
-    const uint32_t slot_bytes = 2u * row_bytes;
+    const uint32_t slot_bytes = 2u * half_bytes;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < GROUPS * SPG; ++s) bar_init(s_u32(bars + s), 1);
@@ -76,69 +80,83 @@ softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    // rows of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; the j-th of them belongs to group j % GROUPS, and the k-th
-    // row of a group (j = g + k * GROUPS) uses the group's slot k % SPG
+    // rows of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; the j-th of them belongs to group j % GROUPS.  A group walks
+    // its rows as UNITS (row k / HALVES, half k % HALVES); unit k uses the group's slot k % SPG
     const long long first = blockIdx.x, step = gridDim.x;
     const long long mine = first < rows ? (rows - first + step - 1) / step : 0;
     const int g = threadIdx.x / GT, t = threadIdx.x % GT, w = t >> 5, lane = t & 31;
-    const long long gmine = mine > g ? (mine - g + GROUPS - 1) / GROUPS : 0;
+    const long long gmine = (mine > g ? (mine - g + GROUPS - 1) / GROUPS : 0) * HALVES;
     unsigned char* const gring = ring + (size_t)g * SPG * slot_bytes;
     const uint32_t gbar = s_u32(bars + g * SPG);
+    // bytes of each half: whole 16-byte pairs (the tail pair may reach into the row padding)
+    const unsigned cols0 = HALVES == 2 ? HALF_COLS : cols, cols1 = HALVES == 2 ? cols - HALF_COLS : 0u;
+    const unsigned bytes0 = (cols0 + 1) / 2 * 16, bytes1 = (cols1 + 1) / 2 * 16;
 
-    auto arm = [&](long long k) {                      // thread 0 of the group: start the copies of the group's k-th row
+    auto arm = [&](long long k) {                      // thread 0 of the group: start the copies of the group's k-th unit
         const int s = (int)(k % SPG);
-        const long long r = first + (g + k * GROUPS) * step;
+        const int h = (int)(k % HALVES);
+        const long long r = first + (g + (k / HALVES) * GROUPS) * step;
         const uint32_t dst = s_u32(gring) + s * slot_bytes;
-        bar_expect_tx(gbar + 8 * s, slot_bytes);
-        bulk_load(dst, logits + r * z_sr, row_bytes, gbar + 8 * s);
-        bulk_load(dst + row_bytes, labels + r * l_sr, row_bytes, gbar + 8 * s);
+        const unsigned nb = h == 0 ? bytes0 : bytes1;
+        bar_expect_tx(gbar + 8 * s, 2 * nb);
+        bulk_load(dst, logits + r * z_sr + h * HALF_COLS, nb, gbar + 8 * s);
+        bulk_load(dst + half_bytes, labels + r * l_sr + h * HALF_COLS, nb, gbar + 8 * s);
     };
     if (t == 0) {
         for (long long k = 0; k < SPG && k < gmine; ++k) arm(k);
     }
+    double mw = -INFINITY, sew = 0.0, lsum = 0.0, dot = 0.0;      // running state of the current row (per lane; mw per warp)
     for (long long k = 0; k < gmine; ++k) {
         const int s = (int)(k % SPG);
+        const int h = (int)(k % HALVES);
+        const unsigned ncols = h == 0 ? cols0 : cols1;            // columns of this unit
         bar_wait(gbar + 8 * s, (uint32_t)(k / SPG) & 1u);
         const double2* zs = reinterpret_cast<const double2*>(gring + (size_t)s * slot_bytes);
-        const double2* ls = reinterpret_cast<const double2*>(gring + (size_t)s * slot_bytes + row_bytes);
+        const double2* ls = reinterpret_cast<const double2*>(gring + (size_t)s * slot_bytes + half_bytes);
         double z[2 * P];
-        double lsum = 0.0, dot = 0.0;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const unsigned c = 2u * (p * GT + t);
             double2 zv = make_double2(-INFINITY, -INFINITY), lv = make_double2(0.0, 0.0);
-            if (c < cols) { zv = zs[p * GT + t]; lv = ls[p * GT + t]; }
-            if (c + 1 >= cols) { zv.y = -INFINITY; lv.y = 0.0; }      // odd width: the pair's second half is row padding
+            if (c < ncols) { zv = zs[p * GT + t]; lv = ls[p * GT + t]; }
+            if (c + 1 >= ncols) { zv.y = -INFINITY; lv.y = 0.0; }     // odd width: the pair's second half is row padding
             z[2 * p] = zv.x; z[2 * p + 1] = zv.y;
-            if (c < cols) dot += lv.x * zv.x;
-            if (c + 1 < cols) dot += lv.y * zv.y;
+            if (c < ncols) dot += lv.x * zv.x;
+            if (c + 1 < ncols) dot += lv.y * zv.y;
             lsum += lv.x;
             lsum += lv.y;
         }
-        group_sync<GT>(g);                             // the slot is drained: everything the row needs is in registers
+        group_sync<GT>(g);                             // the slot is drained: everything the unit needs is in registers
         if (t == 0 && k + SPG < gmine) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             arm(k + SPG);
         }
-        double m = -INFINITY;
+        double m = mw;
 #pragma unroll
         for (int e = 0; e < 2 * P; ++e) m = fmax(m, z[e]);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-        // fmax skips NaN, exp_nonpos does not: a NaN logit makes `se` NaN without a per-element test (np.max propagates NaN).
-        // A warp that holds nothing but -inf / padding subtracts 0 instead of its max (-inf - -inf would be NaN): se = 0.
+        // fmax skips NaN, exp_nonpos does not: a NaN logit makes the sum NaN without a per-element test (np.max propagates NaN).
+        // A warp that has seen nothing but -inf / padding subtracts 0 instead of its max (-inf - -inf would be NaN): sum = 0.
         const double mm = m == -INFINITY ? 0.0 : m;
+        if (HALVES > 1) sew *= (mw == -INFINITY) ? 0.0 : exp_nonpos(mw - m);   // earlier halves, rescaled to the new warp max
         double se = 0.0;
 #pragma unroll
         for (int e = 0; e < 2 * P; ++e) se += exp_nonpos(z[e] - mm);  // straight-line: the 2P evaluations interleave; padding: exp(-inf) = 0
+        sew += se;
+        mw = m;
+        if (h != HALVES - 1) continue;                 // the row's second half follows in the next unit
+        const long long krow = k / HALVES;
+        se = sew;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             se += __shfl_xor_sync(0xffffffffu, se, off);
             lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
             dot += __shfl_xor_sync(0xffffffffu, dot, off);
         }
-        double (*x)[NW] = xch[g][k & 1];
+        double (*x)[NW] = xch[g][krow & 1];
         if (lane == 0) { x[0][w] = m; x[1][w] = se; x[2][w] = lsum; x[3][w] = dot; }
+        mw = -INFINITY; sew = 0.0; lsum = 0.0; dot = 0.0;
         group_sync<GT>(g);
         if (w == 0) {
             double M = x[0][lane % NW], S = x[1][lane % NW], L = x[2][lane % NW], D = x[3][lane % NW];
@@ -155,24 +173,24 @@ softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const 
             if (lane == 0) {
                 if (Mx == -INFINITY) S = NAN;          // a row of -inf: numpy computes exp(-inf - -inf) = nan
                 const double lse = Mx + log(S);
-                out[(first + (g + k * GROUPS) * step) * o_s] = -(D - lse * L);
+                out[(first + (g + krow * GROUPS) * step) * o_s] = -(D - lse * L);
                 if (!(fabs(L - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
             }
         }
     }
 }
 
-template <int P, int GROUPS, int SPG, int GT>
+template <int P, int GROUPS, int SPG, int GT, int HALVES>
 cudaError_t launch_ring(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st,
                         unsigned grid, unsigned row_bytes) {
     static bool attr_set = false;                      // one host thread per device
     const int smem = GROUPS * SPG * 2 * (int)row_bytes;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(softmax_ce_ring_kernel<P, GROUPS, SPG, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCE_RING_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(softmax_ce_ring_kernel<P, GROUPS, SPG, GT, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCE_RING_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    softmax_ce_ring_kernel<P, GROUPS, SPG, GT><<<grid, GROUPS * GT, smem, st>>>(
+    softmax_ce_ring_kernel<P, GROUPS, SPG, GT, HALVES><<<grid, GROUPS * GT, smem, st>>>(
         static_cast<const double*>(labels->ptr), labels->stride[0], static_cast<const double*>(logits->ptr), logits->stride[0],
         static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], (unsigned)logits->shape[1], row_bytes, flag);
     return cudaGetLastError();
@@ -191,15 +209,17 @@ int softmax_ce_ring_try(const adb_tensor* labels, const adb_tensor* logits, cons
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     // Measured per width (tools/bench_sce.py, profiles/r01_softmax_ce_ab.log): the ring wins where a row is too big for two
-    // resident register-kernel CTAs to overlap (2048 < cols <= 4096: 0.83 vs 0.60-0.75 of the HBM roof); up to 2048 columns
-    // the register-resident kernel is as fast or faster (0.87 at 2048), beyond 4096 a slot pair no longer fits three times.
+    // resident register-kernel CTAs to overlap (2048 < cols <= 4096: 0.83-0.87 vs 0.60-0.75 of the HBM roof); up to 2048 columns
+    // the register-resident kernel is as fast or faster (0.87 at 2048); beyond 4096 a whole row no longer fits a slot three
+    // times, so up to 8192 columns a row goes through as two half-rows.
     // A persistent grid also needs several rows per SM.
-    if (cols <= 2048 || cols > 4096 || rows < 4LL * sms) return -1;
-    const unsigned row_bytes = (unsigned)((cols + 1) / 2 * 16);       // whole 16-byte pairs (the tail pair may reach into the row padding)
+    if (cols <= 2048 || cols > 8192 || rows < 4LL * sms) return -1;
     const unsigned grid = (unsigned)(rows < sms ? rows : sms);
-    cudaError_t e;                                                    // slots of 2 * row_bytes fill the 192 KB ring
-    if (cols <= 3072) e = launch_ring<12, 4, 1, 128>(labels, logits, out, flag, st, grid, row_bytes);   // 4 x 48 KB
-    else e = launch_ring<16, 3, 1, 128>(labels, logits, out, flag, st, grid, row_bytes);                // 3 x 64 KB
+    cudaError_t e;                                                    // slots of 2 * half_bytes fill the 192 KB ring
+    if (cols <= 3072) e = launch_ring<12, 4, 1, 128, 1>(labels, logits, out, flag, st, grid, (unsigned)((cols + 1) / 2 * 16));   // 4 x 48 KB
+    else if (cols <= 4096) e = launch_ring<16, 3, 1, 128, 1>(labels, logits, out, flag, st, grid, (unsigned)((cols + 1) / 2 * 16));   // 3 x 64 KB
+    else if (cols <= 6144) e = launch_ring<12, 4, 1, 128, 2>(labels, logits, out, flag, st, grid, 3072u * 8u);     // 4 x 48 KB, a row = two half-rows
+    else e = launch_ring<16, 3, 1, 128, 2>(labels, logits, out, flag, st, grid, 4096u * 8u);          // 3 x 64 KB, a row = two half-rows
     if (e != cudaSuccess) return set_error("softmax_ce ring launch failed: %s", cudaGetErrorString(e));
     count_launch();
     return 0;

@@ -435,9 +435,10 @@ def test_softmax_ce_wide_rows(cols, ad):
         ad.SoftmaxCEWithLogits(labels=ad.Variable(bad, name="l"), logits=ad.Variable(z, name="z"))()
 
 
-@pytest.mark.parametrize("cols", [1024, 2048, 2049, 2500, 3001, 3072, 3073, 4095, 4096])
+@pytest.mark.parametrize("cols", [1024, 2048, 2049, 2500, 3001, 3072, 3073, 4095, 4096, 4097, 4100, 5001, 6144, 8191, 8192])
 def test_softmax_ce_ring_rows(cols, ad):
-    """Persistent bulk-copy ring kernel (csrc/softmax_ce_ring.cu: rows >= 4 per SM, 2048 < cols <= 4096): against the oracle,
+    """Persistent bulk-copy ring kernel (csrc/softmax_ce_ring.cu: rows >= 4 per SM, 2048 < cols <= 8192; beyond 4096 columns a
+    row travels as two half-rows with a running log-sum-exp): against the oracle,
     against the register-resident kernels (ADB_SCE_RING=0), NaN / -inf rows, label validation, pitched row views."""
     rng = np.random.default_rng(cols)
     rows = 4 * 148 + 41
@@ -467,9 +468,15 @@ def test_softmax_ce_ring_rows(cols, ad):
     z[9, :] = -np.inf
     z[11, 3] = np.inf
     z[13, :] = -np.inf; z[13, 5] = np.nan; z[13, 200] = 1.0       # the NaN's warp holds nothing else but -inf
+    z[15, cols - 3] = np.nan                                      # (in the second half-row when cols > 4096)
+    z[17, :cols // 2] = -np.inf                                   # a first half of nothing but -inf: still a finite result
+    z[19, cols // 2:] = -np.inf
     got = run(z, lab)
-    assert np.isnan(got[5]) and np.isnan(got[9]) and np.isnan(got[11]) and np.isnan(got[13])
+    assert np.isnan(got[5]) and np.isnan(got[9]) and np.isnan(got[11]) and np.isnan(got[13]) and np.isnan(got[15])
     assert not np.isnan(got[4]) and not np.isnan(got[rows - 1])
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    for r in (17, 19):                                            # (0 * -inf in sum(l*z): the reference's value there is nan or inf too)
+        assert np.isnan(ref[r]) == np.isnan(got[r]) and (np.isnan(ref[r]) or ref[r] == got[r] or abs(got[r] - ref[r]) <= 1e-12 * abs(ref[r]))
     os.environ["ADB_SCE_RING"] = "0"
     try:
         other = run(z, lab)
