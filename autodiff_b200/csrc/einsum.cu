@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "adb_internal.h"
 
 namespace adb {
@@ -183,7 +185,7 @@ static Group collapse_group(std::vector<const Letter*> ls, bool useA, bool useB,
     return g;
 }
 
-static bool try_gemm(const Problem& P, adb_gemm_desc& d) {
+static bool try_gemm(const Problem& P, adb_gemm_desc& d, bool* swapped = nullptr) {
     if (P.n_ops != 2) return false;
     std::vector<const Letter*> B_, M_, N_, K_;
     for (auto& l : P.letters) {
@@ -207,6 +209,7 @@ static bool try_gemm(const Problem& P, adb_gemm_desc& d) {
     if (gm.sa < 0 || gk.sa < 0 || gk.sb < 0 || gn.sb < 0 || gm.sc < 0 || gn.sc < 0) return false;
     d.batch = gb.extent;
     d.K = gk.extent;
+    if (swapped) *swapped = !(gn.sc <= gm.sc);
     if (gn.sc <= gm.sc) {
         d.M = gm.extent; d.N = gn.extent;
         d.A = P.op[0]; d.a_sm = gm.sa; d.a_sk = gk.sa; d.a_sb = gb.sa;
@@ -290,6 +293,54 @@ static int run_reduce(const Problem& P, cudaStream_t st, std::string* desc) {
     return reduce_run(S, st);
 }
 
+// ---- ragged edge of a GEMM ------------------------------------------------------------------------------------------
+// The NN bias trick (reference high_level_ops.py:32-35) makes one GEMM dimension 4097: a 33rd (65th) column of tiles that
+// is 1/128 (1/64) full.  With ~7-14 tiles per SM that extra column usually costs a whole extra WAVE: at 4097 x 4096 x 8192
+// the busiest SMs run 8 tiles of 128x128 instead of 7 (+14 %; ncu on the 1024-row shard: SMs idle 14 % of the launch).
+// When cutting the <= 4 ragged rows/columns off saves more than they cost as a bandwidth-bound reduction (one pass over
+// the other operand), the contraction runs as  GEMM on the aligned part  +  run_reduce on the edge.
+// Time model: 64x64 k-tile units per SM (a 128x128 tile = 4 units), tile choice as in gemm_f64.cu.
+static double gemm_makespan_units(long long M, long long N) {
+    const long long big = ((M + 127) / 128) * ((N + 127) / 128);
+    const double waste_big = (double)((big + 147) / 148 * 148) / (double)big;
+    if (waste_big <= 1.05) return 4.0 * (double)((big + 147) / 148);
+    const long long small = ((M + 63) / 64) * ((N + 63) / 64);
+    return (double)((small + 147) / 148);
+}
+
+// Which letter (index into P.letters) to cut and by how much; -1 = no split.
+static int ragged_edge(const Problem& P, const adb_gemm_desc& d, bool swapped, long long* edge_len) {
+    if (d.batch != 1 || d.K < 512 || g_precision != 0) return -1;
+    if (const char* e = getenv("ADB_EDGE_SPLIT")) if (e[0] == '0') return -1;      // A/B hook (tools/bench_edge_split.py)
+    if (d.N <= 32 || d.M <= 32) return -1;                    // tall-skinny problems have their own tile configurations
+    const double unit_s = 64.0 * 64.0 * (double)d.K * 2.0 / (37.0e12 / 148.0);      // one 64x64xK tile on one SM
+    const double full = gemm_makespan_units(d.M, d.N);
+    int best = -1;
+    double best_gain = 0.0;
+    for (int side = 0; side < 2; ++side) {                    // 0: letters only operand 0 and the output carry, 1: operand 1
+        int idx = -1, count = 0;
+        for (int i = 0; i < (int)P.letters.size(); ++i) {
+            const Letter& l = P.letters[i];
+            if (l.in_out && l.present[side] && !l.present[1 - side]) { idx = i; ++count; }
+        }
+        if (count != 1) continue;
+        const bool is_m = (side == 0) != swapped;             // does this letter play the GEMM's M role?
+        // Measured (tools/bench_edge_split.py, profiles/r01_edge_split_ab.log): cutting ragged COLUMNS pays (dX of a 4096-wide
+        // layer: 1.117 -> 0.997 ms at 1024 rows, 7.85 -> 7.71 ms at 8192), cutting ragged ROWS does not (dW 8.29 -> 8.52 ms:
+        // the kernel's all-padding warps of an edge row tile already skip their MMAs) - so only the N role is cut.
+        if (is_m) continue;
+        const long long X = P.letters[idx].extent, other = d.M;
+        if (X != d.N) continue;
+        const long long r = X % 128;
+        if (r == 0 || r > 4 || X < 1024) continue;
+        const double main_units = gemm_makespan_units(d.M, X - r);
+        const double edge_s = (double)r * 8.0 * (double)other * (double)d.K / 5.0e12 + 10e-6;
+        const double gain = (full - main_units) * unit_s - 1.5 * edge_s;
+        if (gain > best_gain) { best_gain = gain; best = idx; *edge_len = r; }
+    }
+    return best;
+}
+
 static int run_problem(const Problem& P, cudaStream_t st, std::string* desc) {
     if (P.empty_out) { if (desc) *desc = "empty"; return 0; }
     if (P.empty_sum) return run_fill_zero(P, st, desc);
@@ -298,18 +349,43 @@ static int run_problem(const Problem& P, cudaStream_t st, std::string* desc) {
     if (!has_sum) return run_product(P, st, desc);
     adb_gemm_desc d;
     memset(&d, 0, sizeof d);
-    if (try_gemm(P, d)) {
+    bool swapped = false;
+    if (try_gemm(P, d, &swapped)) {
         if (desc) {
             char b[256];
             snprintf(b, sizeof b, "gemm M=%lld N=%lld K=%lld batch=%lld a=(%lld,%lld,%lld) b=(%lld,%lld,%lld) c=(%lld,%lld,%lld)%s",
                      (long long)d.M, (long long)d.N, (long long)d.K, (long long)d.batch, (long long)d.a_sm, (long long)d.a_sk, (long long)d.a_sb,
                      (long long)d.b_sk, (long long)d.b_sn, (long long)d.b_sb, (long long)d.c_sm, (long long)d.c_sn, (long long)d.c_sb,
-                     d.A == P.op[1] ? " swapped" : "");
+                     swapped ? " swapped" : "");
             *desc = b;
+            long long r = 0;
+            const int cut = ragged_edge(P, d, swapped, &r);
+            if (cut >= 0) {
+                snprintf(b, sizeof b, " + edge reduce of %lld along '%c'", r, P.letters[cut].c);
+                *desc += b;
+            }
             return 0;
         }
         // the 3xTF32 tcgen05 variant only pays off (and only has tiles) for reasonably large contractions
         if (g_precision == 1 && d.M >= 64 && d.N >= 64 && d.K >= 32) return gemm_tf32x3(&d, st);
+        long long r = 0;
+        const int cut = ragged_edge(P, d, swapped, &r);
+        if (cut >= 0) {
+            Problem main = P, edge = P;
+            const Letter& l = P.letters[cut];
+            main.letters[cut].extent = l.extent - r;
+            adb_gemm_desc dm;
+            memset(&dm, 0, sizeof dm);
+            if (try_gemm(main, dm)) {
+                for (int t = 0; t < P.n_ops; ++t)
+                    if (l.present[t]) edge.op[t] = P.op[t] + (l.extent - r) * l.s[t];
+                edge.out = P.out + (l.extent - r) * l.os;
+                if (r == 1) edge.letters.erase(edge.letters.begin() + cut);      // (Problem keeps letters of extent > 1 only)
+                else edge.letters[cut].extent = r;
+                if (int rc = gemm_f64(&dm, st, 0)) return rc;
+                return run_reduce(edge, st, nullptr);
+            }
+        }
         return gemm_f64(&d, st, 0);
     }
     return run_reduce(P, st, desc);

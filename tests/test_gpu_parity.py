@@ -291,6 +291,42 @@ def test_gemm_c_abi_all_layouts(ad):
                     check(Ct.cpu().numpy(), A @ B, what="gemm %s path %d" % ((M, N, K, nb, a_kc, b_kc), path))
 
 
+@pytest.mark.parametrize("spec,shapes", [
+    ("ik,jk->ij", [(1152, 1024), (1027, 1024)]), ("ij,jk->ik", [(1152, 1024), (1024, 1028)]), ("ij,jk->ki", [(2050, 768), (768, 1152)]),
+    ("ik,jk->ij", [(1152, 1024), (2049, 1024)]), ("ij,jk->ik", [(1152, 640), (640, 2050)]),
+])
+def test_gemm_ragged_edge_split(spec, shapes, ad):
+    """Contractions whose M or N is a few elements past a tile multiple: aligned part on the DMMA GEMM, the ragged rows / columns
+    as a reduction (csrc/einsum.cu: ragged_edge) - values, both gradients, and a transposed / sliced operand view."""
+    import ctypes as C
+    from autodiff_b200 import _lib
+    rng = np.random.default_rng(len(spec) + shapes[0][0])
+    a, b = [rng.standard_normal(sh) for sh in shapes]
+    da, db_ = ad.to_device(a), ad.to_device(b)
+    ta, tb = da.tensor(), db_.tensor()
+    ref = np.einsum(spec, a, b)
+    do = ad.DeviceArray.empty(ref.shape)
+    to = do.tensor()
+    buf = C.create_string_buffer(512)
+    _lib.check(_lib.lib().adb_einsum_describe(spec.encode(), 2, (_lib.Tensor * 2)(ta, tb), C.byref(to), buf, 512))
+    assert b"edge reduce" in buf.value, buf.value       # the case really takes the split path
+    for m in (onp, ad):
+        A, B = m.Variable(a, name="a"), m.Variable(b, name="b")
+        e = m.Einsum(spec, A, B)
+        outs = [e] + m.grad(e, [A, B])
+        if m is ad:
+            got = [np.asarray(o()) for o in outs]
+        else:
+            want = [np.asarray(o()) for o in outs]
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        check(g, w)
+    at = np.ascontiguousarray(a.T)                       # the same values through a transposed view of the first operand
+    sa = spec.split(",")[0]
+    spec_t = sa[::-1] + spec[len(sa):]
+    check(np.asarray(ad.Einsum(spec_t, ad.Variable(at, name="at"), ad.Variable(b, name="b"))()), want[0])
+
+
 def test_large_gemm_properties(ad):
     """BASELINE-size contraction checked through size-independent properties: linearity in A and a checksum
     identity  ones^T (A B) ones == (ones^T A)(B ones)."""

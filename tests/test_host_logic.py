@@ -135,9 +135,10 @@ def _tensor(shape, strides=None, ptr=0x10000):
     return _lib.make_tensor(ptr, shape, strides)
 
 
-def _describe(spec, shapes, out_shape, strides=None, out_strides=None):
+def _describe(spec, shapes, out_shape, strides=None, out_strides=None, ptrs=None):
     n = len(shapes)
-    tin = (_lib.Tensor * n)(*[_tensor(s, None if strides is None else strides[i], 0x10000 * (i + 1)) for i, s in enumerate(shapes)])
+    tin = (_lib.Tensor * n)(*[_tensor(s, None if strides is None else strides[i], 0x10000 * (i + 1) if ptrs is None else ptrs[i])
+                              for i, s in enumerate(shapes)])
     tout = _tensor(out_shape, out_strides, 0x900000)
     buf = C.create_string_buffer(512)
     _lib.check(_lib.lib().adb_einsum_describe(spec.encode(), n, tin, C.byref(tout), buf, 512))
@@ -203,3 +204,25 @@ def test_planner_gemm_stride_algebra(spec, shapes):
     assert desc.startswith("gemm"), desc
     _gemm_from_desc(desc, ops, out)
     np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_einsum_plans_cut_the_ragged_edge_of_a_gemm():
+    """The NN bias trick makes one GEMM dimension 4097: when a 65th / 33rd COLUMN of tiles would cost an extra wave, the planner
+    runs the aligned part as a GEMM and the <= 4 ragged columns as a bandwidth-bound reduction (einsum.cu: ragged_edge)."""
+    dx = _describe("ik,jk->ij", [(8192, 4096), (4097, 4096)], (8192, 4097))
+    assert dx.startswith("gemm M=8192 N=4097 K=4096") and dx.endswith("+ edge reduce of 1 along 'j'")
+    assert "edge" in _describe("ik,jk->ij", [(1024, 4096), (4097, 4096)], (1024, 4097))       # one rank's shard at 8 GPUs
+    assert _describe("ij,jk->ik", [(1152, 1024), (1024, 1028)], (1152, 1028)).endswith("+ edge reduce of 4 along 'k'")
+    assert _describe("ij,jk->ki", [(2050, 768), (768, 1152)], (1152, 2050)).endswith("swapped + edge reduce of 2 along 'i'")
+    # the same array as both operands: roles must not be told apart by pointer
+    same = _describe("ik,jk->ij", [(1152, 1024), (1027, 1024)], (1152, 1027), ptrs=(0x10000, 0x10000))
+    assert same.endswith("+ edge reduce of 3 along 'j'")
+    # no cut: ragged ROWS (measured slower), the ragged dimension is the contracted one, aligned problems, a wide remainder,
+    # tall-skinny and batched problems
+    assert "edge" not in _describe("ij,ik->jk", [(8192, 4097), (8192, 4096)], (4097, 4096))
+    assert "edge" not in _describe("ij,jk->ik", [(4098, 4096), (4096, 4096)], (4098, 4096))
+    assert "edge" not in _describe("ij,jk->ik", [(8192, 4097), (4097, 4096)], (8192, 4096))
+    assert "edge" not in _describe("ij,jk->ik", [(8192, 8192), (8192, 8192)], (8192, 8192))
+    assert "edge" not in _describe("ij,jk->ik", [(4096, 4096), (4096, 4160)], (4096, 4160))
+    assert "edge" not in _describe("ij,jk->ik", [(4097, 4096), (4096, 16)], (4097, 16))
+    assert "edge" not in _describe("bij,bjk->bik", [(4, 1024, 1024), (4, 1024, 1025)], (4, 1024, 1025))
