@@ -328,12 +328,13 @@ static int ragged_edge(const Problem& P, const adb_gemm_desc& d, bool swapped, l
         // Measured (tools/bench_edge_split.py, profiles/r01_edge_split_ab.log): cutting ragged COLUMNS pays (dX of a 4096-wide
         // layer: 1.117 -> 0.997 ms at 1024 rows, 7.85 -> 7.71 ms at 8192), cutting ragged ROWS does not (dW 8.29 -> 8.52 ms:
         // the kernel's all-padding warps of an edge row tile already skip their MMAs) - so only the N role is cut.
-        if (is_m) continue;
-        const long long X = P.letters[idx].extent, other = d.M;
-        if (X != d.N) continue;
+        static const bool rows_too = getenv("ADB_EDGE_SPLIT") && getenv("ADB_EDGE_SPLIT")[0] == '2';     // experiments only
+        if (is_m && !rows_too) continue;
+        const long long X = P.letters[idx].extent, other = is_m ? d.N : d.M;
+        if (X != (is_m ? d.M : d.N)) continue;
         const long long r = X % 128;
         if (r == 0 || r > 4 || X < 1024) continue;
-        const double main_units = gemm_makespan_units(d.M, X - r);
+        const double main_units = is_m ? gemm_makespan_units(X - r, d.N) : gemm_makespan_units(d.M, X - r);
         const double edge_s = (double)r * 8.0 * (double)other * (double)d.K / 5.0e12 + 10e-6;
         const double gain = (full - main_units) * unit_s - 1.5 * edge_s;
         if (gain > best_gain) { best_gain = gain; best = idx; *edge_len = r; }
