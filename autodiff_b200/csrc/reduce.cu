@@ -281,6 +281,23 @@ __device__ __forceinline__ void red_walk(const Red3Params& P, const double* cons
     }
 }
 
+// What one thread per output does with the finished sum: the factored-out operand (its offset is decoded here, off the hot
+// path: keeping a running offset in the main loop's prologue cost the 'ijkl,jl->ik' kernel 19 %) or the root.
+__device__ __noinline__ double red_post(const Red3Params& P, unsigned o, double v) {
+    if (P.post) {
+        long long off = 0;
+        unsigned rem = o;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned qn = fd_div(rem, P.odiv[k]);
+            off += (long long)(rem - qn * P.odiv[k].d) * P.post_os[k];
+            rem = qn;
+        }
+        return v * __ldg(P.post + off);
+    }
+    return P.post_sqrt ? sqrt(v) : v;
+}
+
 template <int G, int NOPS, int VEC>
 __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Red3Params P) {
     constexpr int GROUPS = 256 / G;
@@ -292,7 +309,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
     const unsigned hi = (lo + P.chunk < P.R) ? lo + P.chunk : P.R;
 
     unsigned rem = live ? o : 0;
-    long long out_off = 0, post_off = 0;
+    long long out_off = 0;
     const double* base[NOPS];
 #pragma unroll
     for (int t = 0; t < NOPS; ++t) base[t] = P.op[t];
@@ -302,7 +319,6 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
         const unsigned i = rem - qn * P.odiv[k].d;
         rem = qn;
         out_off += (long long)i * P.out_s[k];
-        post_off += (long long)i * P.post_os[k];
 #pragma unroll
         for (int t = 0; t < NOPS; ++t) base[t] += (long long)i * P.op_os[t][k];
     }
@@ -326,7 +342,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
         }
     }
     if (P.splits == 1) {
-        if (lane == 0 && live) P.out[out_off] = P.post ? a * __ldg(P.post + post_off) : (P.post_sqrt ? sqrt(a) : a);
+        if (lane == 0 && live) P.out[out_off] = red_post(P, o, a);
         return;
     }
     if (lane == 0 && live) P.partial[(long long)z * P.NG + o] = a;
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(256) red_row_kernel(const __grid_constant__ Re
             for (int w = 0; w < 8; ++w) t += warp_fin[w];
         }
     }
-    if (lane == 0) P.out[out_off] = P.post ? t * __ldg(P.post + post_off) : (P.post_sqrt ? sqrt(t) : t);
+    if (lane == 0) P.out[out_off] = red_post(P, o, t);
 }
 
 template <int WR, int NOPS, int VEC>
