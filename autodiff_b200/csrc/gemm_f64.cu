@@ -93,6 +93,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
@@ -104,7 +110,7 @@ struct GemmParams {
     int M, N, K;
     int tiles_m, tiles_n;
     int kt_per_split;            // k-tiles each blockIdx.z handles (split-K); == all k-tiles when gridDim.z == 1
-    int _pad;
+    int blocked;                 // bit 0 / 1: the MN-contiguous A / B operand has a BLOCKED tensor map (one TMA box per tile)
     double* C;
     long long c_sm, c_sn, c_sb, c_ss;   // c_ss: stride between split-K partial results
 };
@@ -161,12 +167,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int k0 = (kt_first + kt) * BK;
         if (A_KC) {
             tma_load_3d(sa, &tmA, fb, k0, m0, batch);
+        } else if (p.blocked & 1) {
+            tma_load_4d(sa, &tmA, fb, 0, k0, m0 / 16, batch);          // the BM/16 blocks of [16 k][16 m] in ONE box
         } else {
 #pragma unroll
             for (int b = 0; b < BM / 16; ++b) tma_load_3d(sa + b * 2048, &tmA, fb, m0 + 16 * b, k0, batch);
         }
         if (B_KC) {
             tma_load_3d(sb, &tmB, fb, k0, n0, batch);
+        } else if (p.blocked & 2) {
+            tma_load_4d(sb, &tmB, fb, 0, k0, n0 / 16, batch);
         } else {
 #pragma unroll
             for (int b = 0; b < BN / 16; ++b) tma_load_3d(sb + b * 2048, &tmB, fb, n0 + 16 * b, k0, batch);
@@ -383,6 +393,29 @@ static bool make_tmap(CUtensorMap* map, const double* base, long long inner, lon
     return r == CUDA_SUCCESS;
 }
 
+// An MN-contiguous operand [K rows][MN columns] seen as 4-D: (16 columns, K, MN/16 column blocks, batch), so that ONE box of
+// (16, BK, tile/16, 1) lands in shared memory as the tile/16 blocks of [16 k][16 mn] the fragment loads expect - instead of
+// tile/16 separate 2 KB boxes.  (ncu, 4096x4096x8192: with 16 boxes per k-tile the weight-gradient form ran its tensor pipe at
+// 90.6 % with 1.47 long-scoreboard stall cycles per issue, against 98.1 % / 0.15 for two K-contiguous operands: the TMA unit's
+// per-instruction cost.)  The last column block may reach past MN: the caller guarantees those elements exist (MN % 16 == 0 or
+// the row pitch covers them); what they hold only reaches output rows / columns that are never stored.
+static bool make_tmap_blocked(CUtensorMap* map, const double* base, long long mn, long long K, long long batch,
+                              long long k_stride, long long batch_stride, int box_blocks) {
+    cuuint64_t dims[4] = {16u, (cuuint64_t)K, (cuuint64_t)((mn + 15) / 16), (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)k_stride * 8ull, 128ull, (cuuint64_t)batch_stride * 8ull};
+    cuuint32_t box[4] = {16u, (cuuint32_t)BK, (cuuint32_t)box_blocks, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+static bool blocked_ok(long long mn, long long k_stride) {
+    static int pref = -1;                          // ADB_GEMM_BLOCKED=0: keep the one-box-per-block maps (A/B measurements)
+    if (pref < 0) { const char* e = getenv("ADB_GEMM_BLOCKED"); pref = (e && e[0] == '0') ? 0 : 1; }
+    return pref == 1 && (mn % 16 == 0 || k_stride >= (mn + 15) / 16 * 16);
+}
+
 static bool tma_ok(const double* base, long long s_other, long long s_batch, long long batch) {
     if (reinterpret_cast<uintptr_t>(base) & 15) return false;
     if (s_other <= 0 || (s_other & 1)) return false;
@@ -531,10 +564,13 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws_c), (size_t)splits * batch * M * Np * sizeof(double), st);
             if (e != cudaSuccess) return set_error("gemm: split-K workspace allocation failed: %s", cudaGetErrorString(e));
         }
+        int blocked = 0;
         if (a_kc) ok = make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, bm);
+        else if (blocked_ok(M, d->a_sk) && make_tmap_blocked(&ta, d->A, M, K, batch, d->a_sk, a_bs, bm / 16)) { ok = true; blocked |= 1; }
         else      ok = make_tmap(&ta, d->A, M, K, batch, d->a_sk, a_bs, 16, BK);
         if (ok) {
             if (b_kc) ok = make_tmap(&tb, d->B, K, N, batch, d->b_sn, b_bs, BK, bn);
+            else if (blocked_ok(N, d->b_sk) && make_tmap_blocked(&tb, d->B, N, K, batch, d->b_sk, b_bs, bn / 16)) blocked |= 2;
             else      ok = make_tmap(&tb, d->B, N, K, batch, d->b_sk, b_bs, 16, BK);
         }
         if (ok) {
@@ -542,7 +578,7 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             p.M = (int)M; p.N = (int)N; p.K = (int)K;
             p.tiles_m = (int)((M + bm - 1) / bm);
             p.tiles_n = (int)((N + bn - 1) / bn);
-            p.kt_per_split = kt_per_split; p._pad = 0;
+            p.kt_per_split = kt_per_split; p.blocked = blocked;
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
             int rc;

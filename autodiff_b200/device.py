@@ -104,15 +104,18 @@ class DeviceArray:
     # ---- construction
     @staticmethod
     def empty(shape):
-        """Row pitch of >=2-D arrays is padded to a multiple of 4 elements so every row is 32-byte aligned
+        """Row pitch of >=2-D arrays is padded to a multiple of 4 elements (16 for rows of >= 256) so every row is 32-byte aligned
         (TMA global strides must be multiples of 16 B, the elementwise kernels use 256-bit accesses; the NN bias
         trick makes odd widths like 4097 common, reference high_level_ops.py:32-35)."""
         _ensure_init()
         shape = tuple(int(s) for s in shape)
         t = torch()
         if len(shape) >= 2:
-            # short innermost extents (channels of an NHWC image) are never TMA rows: keep them dense
-            pitch = shape[-1] + (-shape[-1] % 4) if shape[-1] >= 16 else shape[-1]
+            # short innermost extents (channels of an NHWC image) are never TMA rows: keep them dense.  Wide rows are padded to
+            # whole 128-byte lines (16 elements): the blocked tensor map of an MN-contiguous GEMM operand (gemm_f64.cu:
+            # make_tmap_blocked) reads 16-column blocks, and the last block of a 4097-wide row must stay inside the row
+            w = shape[-1]
+            pitch = w + (-w % 16) if w >= 256 else (w + (-w % 4) if w >= 16 else w)
             n = pitch
             for s in shape[:-1]:
                 n *= s
