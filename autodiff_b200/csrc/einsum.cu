@@ -325,11 +325,12 @@ static int ragged_edge(const Problem& P, const adb_gemm_desc& d, bool swapped, l
         }
         if (count != 1) continue;
         const bool is_m = (side == 0) != swapped;             // does this letter play the GEMM's M role?
-        // Measured (tools/bench_edge_split.py, profiles/r01_edge_split_ab.log): cutting ragged COLUMNS pays (dX of a 4096-wide
-        // layer: 1.117 -> 0.997 ms at 1024 rows, 7.85 -> 7.71 ms at 8192), cutting ragged ROWS does not (dW 8.29 -> 8.52 ms:
-        // the kernel's all-padding warps of an edge row tile already skip their MMAs) - so only the N role is cut.
-        static const bool rows_too = getenv("ADB_EDGE_SPLIT") && getenv("ADB_EDGE_SPLIT")[0] == '2';     // experiments only
-        if (is_m && !rows_too) continue;
+        // Measured (tools/bench_edge_split.py, profiles/r01_edge_split_ab.log): ragged COLUMNS: dX of a 4096-wide layer
+        // 1.117 -> 0.997 ms at 1024 rows, 7.85 -> 7.71 ms at 8192; ragged ROWS (dW, M = 4097): 8.19 -> 7.73 ms at 8192 rows,
+        // 1.027 -> 1.009 ms at 1024 (with the 8-box tensor maps of the first version the aligned MN-contiguous GEMM itself was
+        // the slow part and the cut lost: 8.29 -> 8.52 ms).  ADB_EDGE_SPLIT=3 restricts the cut to columns again.
+        static const bool cols_only = getenv("ADB_EDGE_SPLIT") && getenv("ADB_EDGE_SPLIT")[0] == '3';
+        if (is_m && cols_only) continue;
         const long long X = P.letters[idx].extent, other = is_m ? d.N : d.M;
         if (X != (is_m ? d.M : d.N)) continue;
         const long long r = X % 128;

@@ -294,6 +294,7 @@ def test_gemm_c_abi_all_layouts(ad):
 @pytest.mark.parametrize("spec,shapes", [
     ("ik,jk->ij", [(1152, 1024), (1027, 1024)]), ("ij,jk->ik", [(1152, 1024), (1024, 1028)]), ("ij,jk->ki", [(2050, 768), (768, 1152)]),
     ("ik,jk->ij", [(1152, 1024), (2049, 1024)]), ("ij,jk->ik", [(1152, 640), (640, 2050)]),
+    ("ij,ik->jk", [(600, 1025), (600, 1152)]), ("ij,jk->ik", [(1026, 640), (640, 1152)]), ("ji,jk->ik", [(900, 2049), (900, 1152)]),
 ])
 def test_gemm_ragged_edge_split(spec, shapes, ad):
     """Contractions whose M or N is a few elements past a tile multiple: aligned part on the DMMA GEMM, the ragged rows / columns

@@ -207,8 +207,8 @@ def test_planner_gemm_stride_algebra(spec, shapes):
 
 
 def test_einsum_plans_cut_the_ragged_edge_of_a_gemm():
-    """The NN bias trick makes one GEMM dimension 4097: when a 65th / 33rd COLUMN of tiles would cost an extra wave, the planner
-    runs the aligned part as a GEMM and the <= 4 ragged columns as a bandwidth-bound reduction (einsum.cu: ragged_edge)."""
+    """The NN bias trick makes one GEMM dimension 4097: when a 65th / 33rd row or column of tiles would cost an extra wave, the
+    planner runs the aligned part as a GEMM and the <= 4 ragged rows / columns as a bandwidth-bound reduction (einsum.cu: ragged_edge)."""
     dx = _describe("ik,jk->ij", [(8192, 4096), (4097, 4096)], (8192, 4097))
     assert dx.startswith("gemm M=8192 N=4097 K=4096") and dx.endswith("+ edge reduce of 1 along 'j'")
     assert "edge" in _describe("ik,jk->ij", [(1024, 4096), (4097, 4096)], (1024, 4097))       # one rank's shard at 8 GPUs
@@ -217,10 +217,10 @@ def test_einsum_plans_cut_the_ragged_edge_of_a_gemm():
     # the same array as both operands: roles must not be told apart by pointer
     same = _describe("ik,jk->ij", [(1152, 1024), (1027, 1024)], (1152, 1027), ptrs=(0x10000, 0x10000))
     assert same.endswith("+ edge reduce of 3 along 'j'")
-    # no cut: ragged ROWS (measured slower), the ragged dimension is the contracted one, aligned problems, a wide remainder,
-    # tall-skinny and batched problems
-    assert "edge" not in _describe("ij,ik->jk", [(8192, 4097), (8192, 4096)], (4097, 4096))
-    assert "edge" not in _describe("ij,jk->ik", [(4098, 4096), (4096, 4096)], (4098, 4096))
+    dw = _describe("ij,ik->jk", [(8192, 4097), (8192, 4096)], (4097, 4096))                    # ragged rows: the weight gradient
+    assert dw.startswith("gemm M=4097 N=4096 K=8192") and dw.endswith("+ edge reduce of 1 along 'j'")
+    assert _describe("ij,jk->ik", [(4098, 4096), (4096, 4096)], (4098, 4096)).endswith("+ edge reduce of 2 along 'i'")
+    # no cut: the ragged dimension is the contracted one, aligned problems, a wide remainder, tall-skinny and batched problems
     assert "edge" not in _describe("ij,jk->ik", [(8192, 4097), (4097, 4096)], (8192, 4096))
     assert "edge" not in _describe("ij,jk->ik", [(8192, 8192), (8192, 8192)], (8192, 8192))
     assert "edge" not in _describe("ij,jk->ik", [(4096, 4096), (4096, 4160)], (4096, 4160))
