@@ -610,13 +610,19 @@ static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
     }
     const long long groups_per_cta = 256 / width;
     const long long blocks_x = (NG + groups_per_cta - 1) / groups_per_cta;
-    // Slicing the summed range: below eight waves of CTAs, slice until the tail is < 1/8 of the run (one-shot grids
-    // of many short CTAs stream best on B200, tools/probe_stream.cu).  Every slice keeps >= 2 trips.
+    // Slicing the summed range: below a few waves of CTAs, slice the summed range (one-shot grids of many short CTAs stream
+    // best on B200, tools/probe_stream.cu).  Every slice keeps >= 2 trips.
     const long long per_trip = (long long)width * RED_U;
     const long long slots = red3_slots(kernel);
     const long long max_splits = Rl / (per_trip * 2) > 0 ? Rl / (per_trip * 2) : 1;
     long long splits = 1;
-    if (blocks_x < 8 * slots) splits = (8 * slots + blocks_x - 1) / blocks_x;
+    // Row kernels: 4 waves (measured, profiles/r01_reduce_waves.log: 'ijkl,jl->ik' 0.322 -> 0.303 ms, 'ab->a' and 'ab->' a little
+    // better too); column kernels: 8 (fewer, longer CTAs help the 256 MiB 'ab->b' but cost 'ijkl,ik->jl' on 2 GiB 10-29 %).
+    // ADB_RED_WAVES overrides both (experiments).
+    static long long waves_env = -1;
+    if (waves_env < 0) { const char* e = getenv("ADB_RED_WAVES"); waves_env = e ? atoll(e) : 0; if (waves_env < 0) waves_env = 0; }
+    const long long waves = waves_env > 0 ? waves_env : (row ? 4 : 8);
+    if (blocks_x < waves * slots) splits = (waves * slots + blocks_x - 1) / blocks_x;
     if (splits > max_splits) splits = max_splits;
     if (splits > 65535) splits = 65535;
     if (splits < 1) splits = 1;
