@@ -511,7 +511,8 @@ def test_softmax_ce_ring_rows(cols, ad):
     got = run(z, lab)
     assert np.isnan(got[5]) and np.isnan(got[9]) and np.isnan(got[11]) and np.isnan(got[13]) and np.isnan(got[15])
     assert not np.isnan(got[4]) and not np.isnan(got[rows - 1])
-    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    with np.errstate(all="ignore"):                               # (the oracle's own inf - inf / 0 * inf warnings on these rows)
+        ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
     for r in (17, 19):                                            # (0 * -inf in sum(l*z): the reference's value there is nan or inf too)
         assert np.isnan(ref[r]) == np.isnan(got[r]) and (np.isnan(ref[r]) or ref[r] == got[r] or abs(got[r] - ref[r]) <= 1e-12 * abs(ref[r]))
     os.environ["ADB_SCE_RING"] = "0"
