@@ -20,9 +20,29 @@ IN, IMM, TMP = _lib.SRC_IN, _lib.SRC_IMM, _lib.SRC_TMP
 MAX_MEMBERS = 24
 
 
+_bshape_cache = {}
+
+
 def broadcast_shapes(*shapes):
     """np.broadcast_shapes for plain tuples/lists (same result, same error), without numpy's dummy-array machinery:
-    this runs once per Add/Mul node and the second-order char-rnn graph has 40 k of them."""
+    this runs once per Add/Mul node and the second-order char-rnn graph has 40 k of them - almost all with one of a
+    handful of shape combinations, so results are memoised (tuples of tuples only: a list shape is not hashable and
+    takes the computation below)."""
+    try:
+        hit = _bshape_cache.get(shapes)
+    except TypeError:
+        hit = None
+    else:
+        if hit is not None:
+            return hit
+        out = _broadcast_shapes(*shapes)
+        if len(_bshape_cache) < 4096 and all(type(sh) is tuple for sh in shapes):
+            _bshape_cache[shapes] = out
+        return out
+    return _broadcast_shapes(*shapes)
+
+
+def _broadcast_shapes(*shapes):
     first = shapes[0]
     same = True
     for sh in shapes:
