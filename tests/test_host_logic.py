@@ -226,3 +226,18 @@ def test_einsum_plans_cut_the_ragged_edge_of_a_gemm():
     assert "edge" not in _describe("ij,jk->ik", [(4096, 4096), (4096, 4160)], (4096, 4160))
     assert "edge" not in _describe("ij,jk->ik", [(4097, 4096), (4096, 16)], (4097, 16))
     assert "edge" not in _describe("bij,bjk->bik", [(4, 1024, 1024), (4, 1024, 1025)], (4, 1024, 1025))
+
+
+def test_every_translation_unit_is_built():
+    """autodiff_b200/build.py lists every .cu of csrc/ (a new kernel file that is not compiled would only show up as an
+    undefined symbol on the GPU box), and the self-test links the same objects."""
+    import os
+    from autodiff_b200 import build
+    csrc = os.path.join(os.path.dirname(build.__file__), "csrc")
+    on_disk = {f for f in os.listdir(csrc) if f.endswith(".cu")}
+    listed = {src for src, _flags, _obj in build.SOURCES}
+    assert on_disk == listed
+    objs = [obj for _src, _flags, obj in build.SOURCES]
+    assert len(objs) == len(set(objs))
+    script = open(os.path.join(os.path.dirname(os.path.dirname(build.__file__)), "tools", "build_selftest.sh")).read()
+    assert "autodiff_b200/build/*.o" in script
