@@ -7,6 +7,7 @@ import ctypes as C
 import numpy as np
 
 from .. import _lib
+from .. import device as _device
 from ..device import DeviceArray, stream_ptr, to_device, torch
 from .node import ConstFill, Node, Variable
 from .utils import gc_paused
@@ -168,14 +169,13 @@ def evaluate_many(tops, on_ready=None):
             scanned = tape.scan(tops, scalar_of, _has_value, _is_device_node)
             if scanned is not None and any(l is None for l in scanned[1]):      # (a graph of leaves only has nothing to replay)
                 order, leaves, sig = scanned
-                sig = (fusion_enabled, Node.epsilon, len(tops)) + sig
+                sig = (fusion_enabled, Node.epsilon, len(tops), _device.kernel_mode[0], _device.kernel_mode[1]) + sig
                 tp, should_record = tape.lookup(sig)
                 if tp is not None and tape.replay(tp, order, leaves, tops, _materialise_leaf, add_pending_flag, on_ready):
                     return
                 if tp is None and should_record:
                     rec = tape.Recorder()
         if rec is not None:
-            from .. import device as _device
             tape._recorder, _lib._call_hook, _device._alloc_hook = rec, rec.on_call, rec.on_alloc
         try:
             plan = _plan([t for t in tops if not _has_value(t)])
@@ -268,7 +268,6 @@ def eval_many(tops):
         instead of queueing behind it, and their results start travelling back while that GEMM is still running;
       * each compute stream has its own download stream, so a result that is ready never waits behind one that is not.
     Values are identical to evaluating the nodes one by one (same kernels, same operands)."""
-    from .. import device as _device
     from ..device import enqueue_download, to_device_async, use_stream
     tops = list(tops)
     t = torch()

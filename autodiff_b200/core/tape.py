@@ -29,6 +29,7 @@ user-defined numpy nodes, unknown node classes or unresolvable pointers are simp
 """
 import bisect
 import ctypes as C
+from math import copysign as _copysign
 import os
 import sys
 
@@ -127,16 +128,20 @@ def scan(tops, scalar_of, has_value, is_device_node):
                 else:
                     s = n.host_scalar()                             # (subclasses: ConstFill._value would MATERIALISE the constant)
                 if s is not None:
-                    add_sig(("s", s))            # folded into programs as an immediate: the VALUE is structure
+                    # folded into programs as an immediate: the VALUE is structure (-0.0 == 0.0 and hashes alike, so the sign
+                    # of a zero is keyed separately; NaN != NaN only costs a tape miss)
+                    add_sig(("s", s) if s != 0.0 else ("s", s, _copysign(1.0, s)))
                     add_leaf(n)                  # (uploaded only if some kernel reads it as a tensor, see build_tape)
                     continue
             d = n._dev
-            if d is not None:
+            if cls is ConstFill and n.fill is not None and n._host is None:
+                # keyed by the fill VALUE even when a one-element device copy already exists: Einsum drops operands that
+                # are all ones (ops.py Einsum._eval_device), so the value decides which kernels run
+                add_sig(("c", n.fill, n._fill_shape, d is not None))
+            elif d is not None:
                 if type(d) is not DeviceArray:
                     return None
                 add_sig(("d", d.shape, d.strides))
-            elif isinstance(n, ConstFill) and n.fill is not None and n._host is None:
-                add_sig(("c", n.fill, n._fill_shape))
             else:
                 v = n._host if n._host is not None else getattr(n, "_value", None)
                 if isinstance(v, DeviceArray):
@@ -506,6 +511,7 @@ def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
     check = _lib.check
     ends = tape.top_ends
     ti = 0
+    st = C.c_void_p(_device.stream_ptr())         # the CURRENT stream (ad.use_stream), not the one of the recording
     while on_ready is not None and ti < len(ends) and ends[ti] == 0:
         on_ready(tops[ti])
         ti += 1
@@ -515,6 +521,7 @@ def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
         args = c.args
         for ai, j, off in c.void_patches:
             args[ai] = C.c_void_p(bases[j] + off)
+        args[-1] = st                             # every compute entry point takes the stream last
         if c.flag_arg >= 0:
             flag = t.zeros(1, dtype=t.int32, device="cuda")
             args[c.flag_arg] = C.c_void_p(flag.data_ptr())

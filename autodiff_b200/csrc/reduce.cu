@@ -487,17 +487,30 @@ static long long red3_slots(Red3Kernel k) {
 }
 
 // Partial-sum workspace: one grow-only buffer per stream (launches on one stream are ordered, so consecutive
-// reductions can reuse it without stream-ordered malloc/free calls between the kernels).
-static double* red3_workspace(cudaStream_t st, size_t bytes) {
+// reductions can reuse it without stream-ordered malloc/free calls between the kernels).  Growing it is stream-ordered
+// (the old buffer is released behind the kernels already queued, nothing blocks).  While the stream is being CAPTURED
+// into a CUDA graph the shared buffer is never used: a graph must not bake a pointer that a later growth would free, so
+// the partials come from cudaMallocAsync / cudaFreeAsync, which turn into memory nodes private to that graph
+// (*transient = the caller frees the buffer behind its kernel).
+static double* red3_workspace(cudaStream_t st, size_t bytes, bool* transient) {
     struct Ws { double* p = nullptr; size_t n = 0; };
     static std::map<cudaStream_t, Ws> ws;
     static std::mutex mu;
+    *transient = false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs != cudaStreamCaptureStatusNone) {
+        double* p = nullptr;
+        if (cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *transient = true;
+        return p;
+    }
     std::lock_guard<std::mutex> lk(mu);
     Ws& w = ws[st];
     if (w.n < bytes) {
-        if (w.p) { cudaStreamSynchronize(st); cudaFree(w.p); w.p = nullptr; w.n = 0; }
+        if (w.p) { cudaFreeAsync(w.p, st); w.p = nullptr; w.n = 0; }
         size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes + bytes / 2;
-        if (cudaMalloc(reinterpret_cast<void**>(&w.p), want) != cudaSuccess) { cudaGetLastError(); w.p = nullptr; return nullptr; }
+        if (cudaMallocAsync(reinterpret_cast<void**>(&w.p), want, st) != cudaSuccess) { cudaGetLastError(); w.p = nullptr; return nullptr; }
         w.n = want;
     }
     return w.p;
@@ -636,13 +649,15 @@ static int reduce3_try(const ReduceSpec& S, cudaStream_t st) {
     P.R = (unsigned)Rl;
     P.chunk = (unsigned)chunk;
     P.splits = (int)splits;
+    bool transient_ws = false;
     if (splits > 1) {
-        P.partial = red3_workspace(st, (size_t)splits * NG * P.fin_vec * sizeof(double));
+        P.partial = red3_workspace(st, (size_t)splits * NG * P.fin_vec * sizeof(double), &transient_ws);
         if (!P.partial) return set_error("reduce: workspace allocation failed");
     }
     dim3 grid((unsigned)blocks_x, (unsigned)splits, 1);
     kernel<<<grid, 256, 0, st>>>(P);
     cudaError_t e = cudaGetLastError();
+    if (transient_ws) cudaFreeAsync(P.partial, st);
     if (e != cudaSuccess) return set_error("reduce launch failed: %s", cudaGetErrorString(e));
     count_launch();
     return 0;

@@ -467,15 +467,25 @@ class precision:
 
     def __enter__(self):
         self.prev = _lib.lib().adb_get_precision()
-        _lib.check(_lib.lib().adb_set_precision(self.mode))
+        _set_precision_code(self.mode)
         return self
 
     def __exit__(self, *a):
-        _lib.check(_lib.lib().adb_set_precision(self.prev))
+        _set_precision_code(self.prev)
+
+
+# Global kernel-selection state of the library, mirrored here so that launch tapes can key on it (a CUDA graph captured
+# under one mode must never be replayed under another): [precision code, elementwise interpreter forced].
+kernel_mode = [0, 0]
+
+
+def _set_precision_code(code):
+    _lib.check(_lib.lib().adb_set_precision(code))
+    kernel_mode[0] = int(code)
 
 
 def set_precision(mode):
-    _lib.check(_lib.lib().adb_set_precision(precision.MODES[mode]))
+    _set_precision_code(precision.MODES[mode])
 
 
 # --------------------------------------------------------------------------------------- diagnostics
@@ -492,3 +502,4 @@ def ewise_stats():
 def force_interpreter(on=True):
     """Runs every elementwise program on the bytecode interpreter (A/B against the catalogued kernels)."""
     _lib.check(_lib.lib().adb_ewise_force_interpreter(1 if on else 0))
+    kernel_mode[1] = 1 if on else 0

@@ -58,7 +58,7 @@ def _optimizer_stream():
     return _opt_stream
 
 
-def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_optimizer=True):
+def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_optimizer=True, _keep=None):
     """One step of examples/feedforward_mnist.py:17-34 on this rank's shard.  x, y: host ndarrays or DeviceArrays.
     With `overlap_optimizer` (and an optimizer that has `update_one`) the update of each parameter is queued on a side
     stream as soon as its gradient is reduced, so the HBM-bound Adam kernels of layer L run under the DMMA-bound backward
@@ -70,6 +70,8 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_o
     sce = SoftmaxCEWithLogits(labels=yv, logits=logits)
     cost = Einsum("i->", sce) / global_batch
     grads = grad(cost, nn.w)
+    if _keep is not None:
+        _keep.extend([cost] + list(grads))
     works = []
     # (worth two stream switches per parameter only when the update kernels are not tiny: >= 1 M elements somewhere)
     overlap = (overlap_optimizer and hasattr(opt, "update_one") and max(math.prod(w.shape) for w in nn.w) >= (1 << 20)
@@ -107,13 +109,29 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_o
         saved = (_lib._call_hook, _device._alloc_hook)
         _lib._call_hook = None
         _device._alloc_hook = lambda base: base.record_stream(main)      # the new weights / moments are read on `main` next step
+        dbg = os.environ.get("ADB_DP_DEBUG", "")
         try:
-            with t.cuda.stream(side):
-                side.wait_event(done)
+            if dbg == "inline":
+                _device._alloc_hook = None
                 if work is not None:
                     work.wait()
+                new_w[k] = opt.update_one(k, nn.w[k], node._dev)
+            elif dbg == "allocmain":
+                _device._alloc_hook = lambda base: base.record_stream(side)
+                side.wait_event(done)
                 _device.use_stream(side)
                 new_w[k] = opt.update_one(k, nn.w[k], node._dev)
+            else:
+                if dbg in ("syncboth", "syncbefore"):
+                    t.cuda.synchronize()
+                with t.cuda.stream(side):
+                    side.wait_event(done)
+                    if work is not None:
+                        work.wait()
+                    _device.use_stream(side)
+                    new_w[k] = opt.update_one(k, nn.w[k], node._dev)
+                if dbg in ("syncboth", "syncafter"):
+                    t.cuda.synchronize()
         finally:
             _device.use_stream(main)
             _lib._call_hook, _device._alloc_hook = saved
