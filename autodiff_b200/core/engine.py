@@ -151,27 +151,38 @@ def _execute(top, plan):
 
 
 _tape_mod = None
+_grad_mod = None      # core/grad.py, bound on first use (it imports ops, which imports this module)
 
 
 def evaluate_many(tops, on_ready=None):
     """Evaluates several graph outputs with one fusion plan (consumer counts span all of them).
     `on_ready(node)` fires as soon as each output's kernels are queued (used to overlap all-reduces).
     Structures seen before are replayed from a launch tape (core/tape.py) instead of being planned again."""
-    global _tape_mod
+    global _tape_mod, _grad_mod
     if _tape_mod is None:
         from . import tape as _t
-        _tape_mod = _t
+        from . import grad as _g
+        _tape_mod, _grad_mod = _t, _g
     tape = _tape_mod
     tops = list(tops)
     with gc_paused():
         rec, sig, scanned = None, None, None
         if tape.ENABLED and kernel_timings is None and tape._recorder is None:
-            scanned = tape.scan(tops, scalar_of, _has_value, _is_device_node)
+            flags = (fusion_enabled, Node.epsilon, len(tops), _device.kernel_mode[0], _device.kernel_mode[1])
+            lazy = None
+            if _grad_mod is not None and _grad_mod.LAZY:
+                # outputs that are still-deferred gradients (core/grad.py): replay their tape from the forward graph's leaves
+                lazy = _grad_mod.lazy_context(tops, flags)
+                if lazy is not None and _grad_mod.lazy_replay(lazy, _materialise_leaf, add_pending_flag, on_ready):
+                    return
+            scanned = tape.scan(tops, scalar_of, _has_value, _is_device_node)       # (walks into deferred gradients: expands them)
             if scanned is not None and any(l is None for l in scanned[1]):      # (a graph of leaves only has nothing to replay)
                 order, leaves, sig = scanned
-                sig = (fusion_enabled, Node.epsilon, len(tops), _device.kernel_mode[0], _device.kernel_mode[1]) + sig
+                sig = flags + sig
                 tp, should_record = tape.lookup(sig)
                 if tp is not None and tape.replay(tp, order, leaves, tops, _materialise_leaf, add_pending_flag, on_ready):
+                    if lazy is not None:
+                        _grad_mod.lazy_learn(lazy, order, leaves, tp)
                     return
                 if tp is None and should_record:
                     rec = tape.Recorder()
@@ -191,6 +202,8 @@ def evaluate_many(tops, on_ready=None):
         if rec is not None:
             built = tape.build_tape(rec, scanned[0], scanned[1], len(tops))
             tape.store(sig, built)
+            if lazy is not None and built is not None:
+                _grad_mod.lazy_learn(lazy, scanned[0], scanned[1], built)
             if built is not None and tape.SELF_CHECK:
                 tape.self_check(built, scanned[0], scanned[1], tops, _materialise_leaf, add_pending_flag)
 

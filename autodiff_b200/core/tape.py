@@ -455,6 +455,8 @@ def _launch_graph(tape, g, order, bases, base_tensors, tops, add_pending_flag, o
     make = DeviceArray._make
     for i, j, off, shape, strides in tape.values:
         n = order[i]
+        if n is None:
+            continue                              # (deferred-gradient replay: interior nodes have no object)
         if j >= n_ext:
             n._dev = make(buf, a0 + slot_off[j - n_ext] + off, shape, strides)
         elif j >= 0:
@@ -502,6 +504,8 @@ def replay(tape, order, leaves, tops, dev_of, add_pending_flag, on_ready):
     make = DeviceArray._make
     for i, j, off, shape, strides in tape.values:
         n = order[i]
+        if n is None:
+            continue                              # (deferred-gradient replay: interior nodes have no object)
         if j >= n_ext:
             n._dev = make(arena, slot_off[j - n_ext] + off, shape, strides)
         elif j >= 0:
@@ -585,3 +589,7 @@ def store(sig, tape):
 def clear():
     _seen.clear()
     _tapes.clear()
+    g = sys.modules.get(__package__ + ".grad")
+    if g is not None:                             # the deferred-gradient memo holds tapes too
+        g._known.clear()
+        g._memo.clear()

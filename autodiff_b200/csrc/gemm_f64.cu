@@ -35,20 +35,25 @@ constexpr int BK = 16;
 // Tile configuration: 8 warps as 2 (M) x 4 (N); warp tile = (BM/2) x (BN/4) = MT x NT fragments of 8x8.
 //   Big   128x128, 6 stages, 1 CTA/SM  : large contractions (C2a/C2b/C3)
 //   Small  64x64,  6 stages, 2 CTAs/SM : problems with fewer than one wave of 128x128 tiles (char-rnn steps)
-template <int BM_, int BN_, int STAGES_, int MINB_, int WM_ = 2, int WN_ = 4>
+template <int BM_, int BN_, int STAGES_, int MINB_, int WM_ = 2, int WN_ = 4, int DBG_ = 0>
 struct TileCfg {
-    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_, DBG = DBG_;
     static constexpr int WM = WM_, WN = WN_;                  // warp grid (WM x WN = 8 consumer warps)
     static constexpr int MT = BM_ / (8 * WM_), NT = BN_ / (8 * WN_);   // 8-wide MMA fragments per warp
     static_assert(WM_ * WN_ == 8 && MT % 2 == 0 && NT % 2 == 0, "warp grid must use 8 warps and even fragment counts");
     static constexpr int A_TILE_BYTES = BM_ * BK * 8;
     static constexpr int B_TILE_BYTES = BN_ * BK * 8;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int PREFETCH = STAGES_ - 2;              // the slot refilled at step kt was released at kt-2: no stall
+    static constexpr int PREFETCH = STAGES_ - 2;              // the slot refilled at step kt was released at the start of step kt-1
     static constexpr int SMEM = STAGES_ * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES_ * 8;
 };
 using CfgBig = TileCfg<128, 128, 6, 1>;
 using CfgSmall = TileCfg<64, 64, 6, 2>;
+// experiment variants (tools/gemm_stress.cu, paths 7-10)
+using CfgSmallSolo = TileCfg<64, 64, 6, 1>;
+using CfgSmall4 = TileCfg<64, 64, 4, 2>;
+using CfgSmallSync = TileCfg<64, 64, 6, 2, 2, 4, 1>;
+using CfgSmallFence = TileCfg<64, 64, 6, 2, 2, 4, 2>;
 // Tall-and-skinny problems (im2col convolutions: M = batch*OH*OW, N = output channels <= 32): all 8 warps stack along M
 // and share the whole 32-column B tile, so no MMA work is spent on padding columns.
 using CfgSkinny = TileCfg<256, 32, 6, 1, 8, 1>;
@@ -212,6 +217,18 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
         mbar_wait(full0 + 8 * s, ph);
+        // Release of the PREVIOUS k-tile's slot.  A slot may go back to the TMA producer only once every LDS that reads it has
+        // COMPLETED, not merely issued.  Arriving at the end of the iteration is not enough: ptxas hoists the arrive above the
+        // last MMAs, right behind the LDS issue, and under heavy L1/LSU traffic from a kernel that shares the SM (the side-stream
+        // Adam update; tools/gemm_stress.cu reproduces it with any HBM-bound kernel) a queued LDS was overtaken by the refill
+        // of its slot - one warp then multiplied a row fragment of the NEXT k-tile (the round-1 data-parallel parity failure).
+        // Here every MMA of iteration kt-1 has issued (the spin loop above is a basic-block boundary, and an MMA issues only
+        // when its LDS operands have landed), so the arrive can be neither early nor hoisted.
+        if (kt > 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * ((kt - 1) % STAGES));
+        }
+        if (Cfg::DBG == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const unsigned char* st = smem + s * STAGE_BYTES;
         const unsigned char* sA = st + a_off;
         const unsigned char* sB = st + b_off;
@@ -267,8 +284,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        if (Cfg::DBG == 1) __syncthreads();
     }
 
     // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
@@ -582,7 +598,15 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
             int rc;
-            if (skinny_s) {
+            if (force_path >= 7 && force_path <= 10 && a_kc && b_kc) {
+                p.tiles_m = (int)((M + 63) / 64); p.tiles_n = (int)((N + 63) / 64);
+                make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, 64);
+                make_tmap(&tb, d->B, K, N, batch, d->b_sn, b_bs, BK, 64);
+                rc = force_path == 7 ? launch_tma<CfgSmallSolo, true, true>(ta, tb, p, (int)batch, splits, st)
+                   : force_path == 8 ? launch_tma<CfgSmall4, true, true>(ta, tb, p, (int)batch, splits, st)
+                   : force_path == 9 ? launch_tma<CfgSmallSync, true, true>(ta, tb, p, (int)batch, splits, st)
+                   : launch_tma<CfgSmallFence, true, true>(ta, tb, p, (int)batch, splits, st);
+            } else if (skinny_s) {
                 if (a_kc && b_kc) rc = launch_tma<CfgSkinnyS, true, true>(ta, tb, p, (int)batch, splits, st);
                 else if (a_kc && !b_kc) rc = launch_tma<CfgSkinnyS, true, false>(ta, tb, p, (int)batch, splits, st);
                 else if (!a_kc && b_kc) rc = launch_tma<CfgSkinnyS, false, true>(ta, tb, p, (int)batch, splits, st);

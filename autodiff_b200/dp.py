@@ -58,23 +58,31 @@ def _optimizer_stream():
     return _opt_stream
 
 
-def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_optimizer=True, _keep=None):
-    """One step of examples/feedforward_mnist.py:17-34 on this rank's shard.  x, y: host ndarrays or DeviceArrays.
-    With `overlap_optimizer` (and an optimizer that has `update_one`) the update of each parameter is queued on a side
-    stream as soon as its gradient is reduced, so the HBM-bound Adam kernels of layer L run under the DMMA-bound backward
-    GEMMs of the layers below it instead of after them (same kernels, same operands: bit-identical results)."""
+def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_optimizer=True):
+    """One step of examples/feedforward_mnist.py:17-34 on this rank's shard.  x, y: host ndarrays or DeviceArrays."""
+    def build_cost():
+        xv = Variable(x, name="images")
+        yv = Variable(y, name="labels")
+        sce = SoftmaxCEWithLogits(labels=yv, logits=nn(xv))
+        return Einsum("i->", sce) / global_batch
+    return step(nn.w, opt, build_cost, dist, read_loss, overlap_optimizer)
+
+
+def step(params, opt, build_cost, dist=None, read_loss=True, overlap_optimizer=True, broadcast_check=False):
+    """One data-parallel training step of ANY model written against the reference API: `build_cost()` returns the loss node
+    of this rank's shard, already divided by the GLOBAL batch (the reference divides by a constant, feedforward_mnist.py:25),
+    `params` are the Variables to train.  Every parameter gradient is all-reduced (sum) in place as soon as its kernels are
+    queued, the optimizer runs replicated.  With `overlap_optimizer` (and an optimizer that has `update_one`) the update of
+    each parameter is queued on a side stream as soon as its gradient is reduced, so the HBM-bound update kernels of layer L
+    run under the DMMA-bound backward GEMMs of the layers below it (same kernels, same operands: bit-identical results -
+    tests/test_gpu_parity.py::test_dp_overlap_schedules_bitwise)."""
     from . import _lib, device as _device
-    xv = Variable(x, name="images")
-    yv = Variable(y, name="labels")
-    logits = nn(xv)
-    sce = SoftmaxCEWithLogits(labels=yv, logits=logits)
-    cost = Einsum("i->", sce) / global_batch
-    grads = grad(cost, nn.w)
-    if _keep is not None:
-        _keep.extend([cost] + list(grads))
+    params = list(params)
+    cost = build_cost()
+    grads = grad(cost, params)
     works = []
     # (worth two stream switches per parameter only when the update kernels are not tiny: >= 1 M elements somewhere)
-    overlap = (overlap_optimizer and hasattr(opt, "update_one") and max(math.prod(w.shape) for w in nn.w) >= (1 << 20)
+    overlap = (overlap_optimizer and opt is not None and hasattr(opt, "update_one") and max(math.prod(w.shape) for w in params) >= (1 << 20)
                and all(isinstance(g, Node) for g in grads))
     new_w = [None] * len(grads)
     if overlap:
@@ -109,29 +117,13 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_o
         saved = (_lib._call_hook, _device._alloc_hook)
         _lib._call_hook = None
         _device._alloc_hook = lambda base: base.record_stream(main)      # the new weights / moments are read on `main` next step
-        dbg = os.environ.get("ADB_DP_DEBUG", "")
         try:
-            if dbg == "inline":
-                _device._alloc_hook = None
+            with t.cuda.stream(side):
+                side.wait_event(done)
                 if work is not None:
                     work.wait()
-                new_w[k] = opt.update_one(k, nn.w[k], node._dev)
-            elif dbg == "allocmain":
-                _device._alloc_hook = lambda base: base.record_stream(side)
-                side.wait_event(done)
                 _device.use_stream(side)
-                new_w[k] = opt.update_one(k, nn.w[k], node._dev)
-            else:
-                if dbg in ("syncboth", "syncbefore"):
-                    t.cuda.synchronize()
-                with t.cuda.stream(side):
-                    side.wait_event(done)
-                    if work is not None:
-                        work.wait()
-                    _device.use_stream(side)
-                    new_w[k] = opt.update_one(k, nn.w[k], node._dev)
-                if dbg in ("syncboth", "syncafter"):
-                    t.cuda.synchronize()
+                new_w[k] = opt.update_one(k, params[k], node._dev)
         finally:
             _device.use_stream(main)
             _lib._call_hook, _device._alloc_hook = saved
@@ -140,25 +132,65 @@ def train_step(nn, opt, x, y, global_batch, dist=None, read_loss=True, overlap_o
     evaluate_many(list(reversed(grads)) + ([cost] if read_loss else []), on_ready=ready)
     for w in works:
         w.wait()
-    if overlap:
+    if opt is None:
+        new_w = None
+    elif overlap:
         main.wait_stream(side)
         for k, g in enumerate(grads):              # (a gradient whose callback never fired: update it here)
             if new_w[k] is None:
-                new_w[k] = opt.update_one(k, nn.w[k], g.eval_device())
+                new_w[k] = opt.update_one(k, params[k], g.eval_device())
         opt.end_step()
     else:
-        new_w = opt(list(nn.w), [g.eval_device() for g in grads])
-    opt.apply_new_weights(nn.w, new_w)
+        new_w = opt(list(params), [g.eval_device() for g in grads])
+    if new_w is not None:
+        opt.apply_new_weights(params, new_w)
     loss = None
     if read_loss:
         lv = cost.eval_device()
         if dist is not None:
+            own = DeviceArray.empty(())            # (never reduce in place into a value that may alias a tape arena / constant)
+            from .device import copy_device
+            copy_device(lv, own)
+            lv = own
             dist.all_reduce(_flat_view(lv), op=dist.ReduceOp.SUM)
         if read_loss == "deferred":
             return PendingLoss(lv)
         loss = float(to_host(lv))
         check_pending_flags()                      # deferred label validation of SoftmaxCEWithLogits (reference ops.py:246-248)
+    if opt is None:
+        return loss, [g.eval_device() for g in grads]
     return loss
+
+
+def sharded_eval(tops, dist=None):
+    """Evaluates nodes whose value is a SUM over the batch rows of this rank's shard (parameter gradients of any order: the
+    second-order `gg` of SURVEY 8e) and all-reduces each in place across the ranks as soon as its kernels are queued.
+    Returns the device arrays (identical on every rank)."""
+    works = []
+
+    def ready(node):
+        if dist is None:
+            return
+        d = node._dev
+        if d.size <= 16 or any(st == 0 and dim > 1 for dim, st in zip(d.shape, d.strides)):
+            from .device import copy_device
+            own = DeviceArray.empty(d.shape)
+            copy_device(d, own)
+            node._dev = d = own
+        works.append(allreduce_async(d, dist))
+    evaluate_many(list(tops), on_ready=ready)
+    for w in works:
+        w.wait()
+    return [t.eval_device() for t in tops]
+
+
+def broadcast_params(params, dist, src=0):
+    """Makes every rank start from rank `src`'s parameter values (ranks otherwise rely on identical seeding)."""
+    if dist is None:
+        return
+    for p in params:
+        d = p.eval_device()
+        dist.broadcast(_flat_view(d), src=src)
 
 
 class PendingLoss:

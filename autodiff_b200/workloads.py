@@ -4,14 +4,15 @@ API (autodiff_b200 or the numpy oracle), so the same builder feeds the GPU arm a
 import numpy as np
 
 
-def conv_net(ad, x, labels, filters1, filters2, dense):
-    """NHWC x -> conv5x5 (VALID) -> ReLU -> conv5x5 -> ReLU -> flatten -> dense -> SoftmaxCE mean."""
+def conv_net(ad, x, labels, filters1, filters2, dense, batch=None):
+    """NHWC x -> conv5x5 (VALID) -> ReLU -> conv5x5 -> ReLU -> flatten -> dense -> SoftmaxCE mean.
+    `batch`: the divisor of the loss (the GLOBAL batch when x is one rank's shard); defaults to the rows of x."""
     n = x.shape[0]
     h1 = ad.ReLU(ad.Conv2D(x, filters1))
     h2 = ad.ReLU(ad.Conv2D(h1, filters2))
     flat = ad.Reshape(h2, (n, -1))
     logits = flat @ dense
-    return ad.Einsum("i->", ad.SoftmaxCEWithLogits(labels=labels, logits=logits)) / n
+    return ad.Einsum("i->", ad.SoftmaxCEWithLogits(labels=labels, logits=logits)) / (n if batch is None else batch)
 
 
 def conv_net_params(rng, c_in=3, c1=16, c2=32, k=5, hw=64, classes=10):

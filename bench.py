@@ -14,8 +14,9 @@ JSON line under "mlp_train".
 value  : inputs resident in HBM, results stay in HBM, CUDA-event timed.
 e2e    : the same sweep through the public API with host buffers: ad.Variable(pinned ndarray) ... node() ->
          ndarray; host->device and device->host copies inside the timed region.
---impl reference : the numpy oracle (oracle/np_autodiff.py, the reference's own algorithm: np.einsum without
-         BLAS, single thread) timed on the host cores on a bounded sample of the same sweep.
+--impl reference : the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.sh; np.einsum without BLAS,
+         single thread) timed on the host cores on a bounded sample of the same sweep; the numpy port
+         oracle/np_autodiff.py stands in only when baseline/_ref is absent.
 """
 import argparse
 import json
@@ -127,7 +128,8 @@ def run_gpu(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
 
     def barrier():
         if dist is not None:
@@ -244,21 +246,13 @@ def run_gpu(args):
                "api": "ad.Variable(pinned ndarray) -> ad.Einsum / ad.grad -> ad.eval_many(nodes) returns host ndarrays "
                       "(== [n() for n in nodes]; H2D, kernels and D2H pipelined on three streams)"}
 
-    mlp = None
+    # ---- the training configs (C1, C3, C4, C5): batch-sharded over all ranks, each with dp_parity + roofline
+    mlp, extra, parity_ok = None, None, True
     if not args.skip_mlp:
-        try:
-            from autodiff_b200 import dp
-            mlp = dp.bench_mlp(args, dist)
-        except Exception as ex:      # reported, never silently dropped
-            mlp = {"error": repr(ex)[:300]}
-
-    extra = None
-    if rank == 0 and world == 1 and not args.skip_mlp:
-        try:
-            from autodiff_b200 import workloads as wl
-            extra = {"c4_conv_b256": wl.bench_conv(ad), "c5_char_rnn_h1024_t128_b512_second_order": wl.bench_char_rnn(ad)}
-        except Exception as ex:
-            extra = {"error": repr(ex)[:300]}
+        from autodiff_b200 import training_bench
+        mlp, extra, parity_ok = training_bench.bench_training(args, dist, ad)
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            attach_cpu_baselines(mlp, extra)
 
     # ---- the TF32 variant of the contraction path (north_star: 1e-4 bar): C2a forward + both grads as 3xTF32 on tcgen05
     tf32 = None
@@ -296,7 +290,7 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = run_reference_sample(reps=1, courtesy=True)
+        cpu = run_reference_sample(reps=2, courtesy=True)
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -313,36 +307,42 @@ def run_gpu(args):
             open(os.environ["ADB_EW_STATS"], "w").write(ad.ewise_stats())
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and not parity_ok:
+        sys.stderr.write("bench.py: a data-parallel parity field is above the 1e-12 bar (or a training config failed); see dp_parity in the line above\n")
+        sys.exit(3)
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
 def run_reference_sample(reps=1, courtesy=False):
-    """The reference's algorithm (numpy oracle = np.einsum without BLAS, single thread) on a bounded sample."""
-    import oracle.np_autodiff as onp
-    rng = np.random.default_rng(1337)
-    inputs = {n: [rng.standard_normal(s) for s in shapes] for n, (spec, shapes) in SAMPLE.items()}
-    flops = sweep_flops(SAMPLE)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        for name, e, da, db in build_sweep(onp, SAMPLE, inputs):
-            for node in (e, da, db):
-                node()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    out = {"value": round(flops / best / 1e12, 6), "unit": "TFLOP/s", "cores": 1, "host_cores_available": os.cpu_count(),
-           "kind": "port", "seconds": round(best, 3),
-           "sample": "same sweep scaled to 'ij,jk->ik' 1536^2, 'bij,bjk->bik' b=16 384^2, 'ijkl,jl->ik' 64^4, fwd + 2 grads each "
-                     "(%.3g flop); np.einsum without optimize is single-threaded C (reference ops.py:180), so more cores do not help it" % flops}
+    """The reference's own implementation (baseline/_ref through baseline/ref_shim.py; the numpy port when that is not
+    installed) of the sweep on a bounded sample: np.einsum without BLAS, single thread (reference ops.py:180)."""
+    from baseline import cpu_arm
+    out = cpu_arm.sweep(SAMPLE, reps=reps)
     if courtesy:
         # NOT the reference path (it never calls BLAS): what all host cores reach on the same matmul through numpy's BLAS
-        a, b = inputs["C2a"]
+        rng = np.random.default_rng(1337)
+        a, b = rng.standard_normal(SAMPLE["C2a"][1][0]), rng.standard_normal(SAMPLE["C2a"][1][1])
         t0 = time.perf_counter()
         _ = a @ b
         dt = time.perf_counter() - t0
         out["blas_all_cores_courtesy"] = {"tflops": round(2.0 * a.shape[0] ** 3 / dt / 1e12, 4), "what": "numpy a @ b (OpenBLAS, all cores) on the 1536^2 member; "
                                           "not what the reference executes"}
     return out
+
+
+def attach_cpu_baselines(mlp, extra):
+    """`cpu_baseline` beside every training number: the reference's own loop timed on this box's host cores (bounded samples)."""
+    from baseline import cpu_arm
+    jobs = [(mlp, "c1_mlp_784_100_10_b64", lambda: cpu_arm.mlp_train([784, 100, 10], 64, steps=30, warmup=3)),
+            (mlp, "c3_mlp_4096x8_b8192", lambda: cpu_arm.mlp_train([4096] * 9, 16, steps=1, warmup=0)),
+            (extra, "c4_conv_b256", lambda: cpu_arm.conv_train(4)),
+            (extra, "c5_char_rnn_h1024_t128_b512_second_order", lambda: cpu_arm.char_rnn_second_order(1024, 16, 64, 71))]
+    for grp, key, fn in jobs:
+        if isinstance(grp, dict) and isinstance(grp.get(key), dict):
+            try:
+                grp[key]["cpu_baseline"] = fn()
+            except Exception as ex:
+                grp[key]["cpu_baseline"] = {"error": repr(ex)[:200]}
 
 
 def run_reference(args):
@@ -362,7 +362,9 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": "TFLOP/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "einsum sweep fp64 (BASELINE configs[1]), bounded sample per step: " + last["sample"]},
+            "config": {"workload": "einsum sweep fp64 (BASELINE configs[1]), bounded sample per step: " + last["sample"],
+                       "reference": "unmodified bgavran/autodiff from baseline/_ref (graphviz stub + tuple-ised slice lists only)"
+                                    if last["kind"] == "reference" else "numpy port oracle/np_autodiff.py (baseline/_ref not installed)"},
             "cpu_baseline": last, "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

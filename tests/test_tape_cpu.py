@@ -2,8 +2,20 @@
 equal for isomorphic graphs and differ whenever the kernels or their wiring would differ."""
 import numpy as np
 
+import pytest
+
 import autodiff_b200 as ad
-from autodiff_b200.core import engine, tape
+from autodiff_b200.core import engine, grad as grad_mod, tape
+
+
+@pytest.fixture(autouse=True)
+def _plain_grad():
+    """These tests compare signatures of EXPANDED gradient graphs: keep `ad.grad` on the plain path (tests/test_lazy_grad_cpu.py
+    covers the deferred one)."""
+    saved = grad_mod.LAZY
+    grad_mod.LAZY = False
+    yield
+    grad_mod.LAZY = saved
 
 
 def _sig(tops):

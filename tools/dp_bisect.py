@@ -201,7 +201,7 @@ def part_d():
         xd, yd = ad.to_device(X[rows[0]:rows[1]]), ad.to_device(Y[rows[0]:rows[1]])
         dp.train_step(nn, opt, xd, yd, GB, None, read_loss=True, overlap_optimizer=overlap)
         keep = []
-        dp.train_step(nn, opt, xd, yd, GB, None, read_loss=True, overlap_optimizer=overlap, _keep=keep)
+        dp.train_step(nn, opt, xd, yd, GB, None, read_loss=True, overlap_optimizer=overlap)
         torch.cuda.synchronize()
         vals = []
         order = walk(keep)

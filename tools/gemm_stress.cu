@@ -31,6 +31,23 @@ __global__ void hammer(const double4* a, const double4* b, const double4* c, con
     z[i] = make_double4(vd.x + va.x, vd.y + va.y, vd.z + va.z, vd.w + va.w);
 }
 
+__global__ void hammer_ro(const double4* a, const double4* b, const double4* c, const double4* d, double4* x, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    double4 va = a[i], vb = b[i], vc = c[i], vd = d[i];
+    if (va.x + vb.x + vc.x + vd.x == 123.456) x[i] = va;      // never true: loads only
+}
+__global__ void hammer_wo(double4* x, double4* y, double4* z, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    x[i] = make_double4(1, 2, 3, 4); y[i] = make_double4(1, 2, 3, 4); z[i] = make_double4(1, 2, 3, 4);
+}
+__global__ void hammer_spin(double* x, int iters) {           // no memory traffic: many short CTAs that only occupy issue slots
+    double v = threadIdx.x;
+    for (int i = 0; i < iters; ++i) v = fma(v, 1.0000001, 1e-9);
+    if (v == 123.456) x[0] = v;
+}
+
 __global__ void count_diff(const unsigned long long* a, const unsigned long long* b, size_t n, unsigned long long* out /*[0]=count,[1]=first index+1*/) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -74,7 +91,11 @@ int main(int argc, char** argv) {
         // queue several GEMMs back to back with hammers interleaved on the other stream (deep queue, like a training step)
         CK(cudaEventRecord(e0, s1));
         for (int rr = 0; rr < 4; ++rr) {
-            if (do_hammer) hammer<<<(unsigned)((HN / 4 + 255) / 256), 256, 0, s2>>>((double4*)h[0], (double4*)h[1], (double4*)h[2], (double4*)h[3], (double4*)h[4], (double4*)h[5], (double4*)h[6], HN / 4);
+            const unsigned hg = (unsigned)((HN / 4 + 255) / 256);
+            if (do_hammer == 2) hammer_ro<<<hg, 256, 0, s2>>>((double4*)h[0], (double4*)h[1], (double4*)h[2], (double4*)h[3], (double4*)h[4], HN / 4);
+            else if (do_hammer == 3) hammer_wo<<<hg, 256, 0, s2>>>((double4*)h[4], (double4*)h[5], (double4*)h[6], HN / 4);
+            else if (do_hammer == 4) hammer_spin<<<hg / 8, 256, 0, s2>>>(h[4], 2000);
+            else if (do_hammer == 1) hammer<<<(unsigned)((HN / 4 + 255) / 256), 256, 0, s2>>>((double4*)h[0], (double4*)h[1], (double4*)h[2], (double4*)h[3], (double4*)h[4], (double4*)h[5], (double4*)h[6], HN / 4);
             d.C = C + (size_t)rr * M * N;
             if (adb_gemm_f64_path(&d, s1, path)) { printf("gemm: %s\n", adb_last_error()); return 2; }
         }
