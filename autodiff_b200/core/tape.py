@@ -52,10 +52,10 @@ GRAPH = os.environ.get("ADB_TAPE_GRAPH", "1") != "0"
 GRAPH_AFTER_REPLAYS = int(os.environ.get("ADB_TAPE_GRAPH_AFTER", "1"))   # call-by-call replays before a tape is captured (0 with
 GRAPH_MIN_CALLS = int(os.environ.get("ADB_TAPE_GRAPH_MIN_CALLS", "4"))   # ADB_TAPE_SELFCHECK=1: every graph of the test-suite)
 GRAPH_MAX_STAGE_BYTES = 64 << 20       # leaves are copied next to the arena on every replay: only worth it when they are small
-# All graph buffers together (they outlive the step).  8 GB keeps the launch-bound small graphs (C1: 25 kernels, 1 MB) and
-# leaves out arenas like the second-order char-rnn's 26 GB, where the graph measured a wash (0.395-0.42 s vs 0.397-0.41 s
-# call by call, profiles/r01_graph_ab.log) while pinning the memory.
-GRAPH_MAX_TOTAL_BYTES = int(os.environ.get("ADB_TAPE_GRAPH_BYTES", str(8 << 30)))
+# All graph buffers together (they outlive the step): 64 GB of the 180 GB.  The second-order char-rnn's arena is 26 GB; while
+# its Python graph build dominated the evaluation its graph measured a wash (profiles/r01_graph_ab.log), but with deferred
+# gradients (core/grad.py) the 9.5 k ctypes calls of a call-by-call replay ARE the host time, and one graph launch removes them.
+GRAPH_MAX_TOTAL_BYTES = int(os.environ.get("ADB_TAPE_GRAPH_BYTES", str(64 << 30)))
 SCE_ERROR = "Labels must be a valid probability distribution!"
 
 _seen = {}               # signature -> sightings so far

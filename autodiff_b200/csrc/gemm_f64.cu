@@ -35,25 +35,23 @@ constexpr int BK = 16;
 // Tile configuration: 8 warps as 2 (M) x 4 (N); warp tile = (BM/2) x (BN/4) = MT x NT fragments of 8x8.
 //   Big   128x128, 6 stages, 1 CTA/SM  : large contractions (C2a/C2b/C3)
 //   Small  64x64,  6 stages, 2 CTAs/SM : problems with fewer than one wave of 128x128 tiles (char-rnn steps)
-template <int BM_, int BN_, int STAGES_, int MINB_, int WM_ = 2, int WN_ = 4, int DBG_ = 0>
+template <int BM_, int BN_, int STAGES_, int MINB_, int WM_ = 2, int WN_ = 4, int PREFETCH_ = STAGES_ - 2>
 struct TileCfg {
-    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_, DBG = DBG_;
+    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_;
     static constexpr int WM = WM_, WN = WN_;                  // warp grid (WM x WN = 8 consumer warps)
     static constexpr int MT = BM_ / (8 * WM_), NT = BN_ / (8 * WN_);   // 8-wide MMA fragments per warp
     static_assert(WM_ * WN_ == 8 && MT % 2 == 0 && NT % 2 == 0, "warp grid must use 8 warps and even fragment counts");
     static constexpr int A_TILE_BYTES = BM_ * BK * 8;
     static constexpr int B_TILE_BYTES = BN_ * BK * 8;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int PREFETCH = STAGES_ - 2;              // the slot refilled at step kt was released at the start of step kt-1
+    // k-tiles in flight ahead of the consumers.  The slot of k-tile t is released when a warp has passed the full-barrier wait of
+    // t+1 (see the main loop), so the slot the producer refills at step kt (tile kt + PREFETCH, last used by kt + PREFETCH - STAGES)
+    // is free once every warp has started step kt + PREFETCH - STAGES + 1: STAGES - PREFETCH - 1 steps of slack between warps.
+    static constexpr int PREFETCH = PREFETCH_;
     static constexpr int SMEM = STAGES_ * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES_ * 8;
 };
 using CfgBig = TileCfg<128, 128, 6, 1>;
 using CfgSmall = TileCfg<64, 64, 6, 2>;
-// experiment variants (tools/gemm_stress.cu, paths 7-10)
-using CfgSmallSolo = TileCfg<64, 64, 6, 1>;
-using CfgSmall4 = TileCfg<64, 64, 4, 2>;
-using CfgSmallSync = TileCfg<64, 64, 6, 2, 2, 4, 1>;
-using CfgSmallFence = TileCfg<64, 64, 6, 2, 2, 4, 2>;
 // Tall-and-skinny problems (im2col convolutions: M = batch*OH*OW, N = output channels <= 32): all 8 warps stack along M
 // and share the whole 32-column B tile, so no MMA work is spent on padding columns.
 using CfgSkinny = TileCfg<256, 32, 6, 1, 8, 1>;
@@ -118,6 +116,8 @@ struct GemmParams {
     int blocked;                 // bit 0 / 1: the MN-contiguous A / B operand has a BLOCKED tensor map (one TMA box per tile)
     double* C;
     long long c_sm, c_sn, c_sb, c_ss;   // c_ss: stride between split-K partial results
+    int tile_offset;             // first tile (raster order) of this launch: the tail wave is a launch of its own
+    int ws_tiles;                // > 0: C is a workspace of [gridDim.z][ws_tiles] dense BM x BN tiles (tail wave, see gemm_tail_fixup)
 };
 
 // ----------------------------------------------------------------------------- TMA + DMMA kernel
@@ -138,7 +138,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     // grouped rasterisation: 8 tile-rows share their B column panels in L2
     const int GROUP = 8;
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x + p.tile_offset;
     const int group_size = GROUP * p.tiles_n;
     const int first_m = (tile / group_size) * GROUP;
     const int gm = min(p.tiles_m - first_m, GROUP);
@@ -228,7 +228,6 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * ((kt - 1) % STAGES));
         }
-        if (Cfg::DBG == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const unsigned char* st = smem + s * STAGE_BYTES;
         const unsigned char* sA = st + a_off;
         const unsigned char* sB = st + b_off;
@@ -284,11 +283,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
         }
-        if (Cfg::DBG == 1) __syncthreads();
     }
 
     // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
-    double* __restrict__ Cb = p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
+    // (tail wave: the partial tile goes to its own dense BM x BN slot of the workspace, addressed by tile-local coordinates)
+    double* __restrict__ Cb = p.ws_tiles > 0
+        ? p.C + ((long long)blockIdx.z * p.ws_tiles + blockIdx.x) * (BM * BN) - ((long long)m0 * BN + n0)
+        : p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int row = m0 + warp_m * (BM / WM) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
@@ -322,6 +323,37 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
         }
+    }
+}
+
+// ----------------------------------------------------------------------------- tail-wave fix-up
+// C tile = sum over the K-slices z (fixed order => deterministic) of the dense BM x BN partial tiles the tail launch wrote.
+__global__ void __launch_bounds__(256)
+gemm_tail_fixup(const double* __restrict__ ws, int splits, int ws_tiles, int bm, int bn, int tile_offset, int tiles_m, int tiles_n,
+                int M, int N, double* __restrict__ C, long long c_sm, long long c_sn) {
+    const int GROUP = 8;
+    const int tile = blockIdx.x + tile_offset;
+    const int group_size = GROUP * tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(tiles_m - first_m, GROUP);
+    const int tm = first_m + (tile % group_size) % gm;
+    const int tn = (tile % group_size) / gm;
+    const int m0 = tm * bm, n0 = tn * bn;
+    const long long tile_elems = (long long)bm * bn;
+    const double* base = ws + (long long)blockIdx.x * tile_elems;
+    const long long zs = (long long)ws_tiles * tile_elems;
+    for (int e = threadIdx.x * 2; e < bm * bn; e += 512) {           // bn is even: a pair never straddles a row
+        const int r = e / bn, c = e - r * bn;
+        const int row = m0 + r, col = n0 + c;
+        if (row >= M || col >= N) continue;
+        double2 acc = *reinterpret_cast<const double2*>(base + e);
+        for (int z = 1; z < splits; ++z) {
+            const double2 v = *reinterpret_cast<const double2*>(base + z * zs + e);
+            acc.x += v.x; acc.y += v.y;
+        }
+        double* cp = C + (long long)row * c_sm + (long long)col * c_sn;
+        cp[0] = acc.x;
+        if (col + 1 < N) cp[c_sn] = acc.y;
     }
 }
 
@@ -440,7 +472,7 @@ static bool tma_ok(const double* base, long long s_other, long long s_batch, lon
 }
 
 template <class Cfg, bool A_KC, bool B_KC>
-static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, int splits, cudaStream_t st) {
+static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, int splits, cudaStream_t st, int ntiles = -1) {
     static bool attr_set = false;
     auto kern = gemm_tma_kernel<Cfg, A_KC, B_KC>;
     constexpr int GEMM_SMEM = Cfg::SMEM;
@@ -449,7 +481,7 @@ static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
         if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
+    dim3 grid((unsigned)(ntiles >= 0 ? ntiles : p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("gemm_tma launch failed: %s", cudaGetErrorString(e));
@@ -545,7 +577,12 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         // short K (<= 8 k-tiles): a CTA is mostly prologue + epilogue, so two 64x64 CTAs per SM that overlap each other beat
         // one 128x128 CTA (conv dX 802816x400x32: 1.38 -> 1.05 ms)
         const bool short_k = (K + BK - 1) / BK <= 8;
-        const bool small = !skinny && !skinny_s && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && (waste_big > 1.05 || short_k)))));
+        // 128x128 tiles whose last wave is at most half full and whose K is long run that wave split along K (below) instead of
+        // falling back to 64x64 tiles: 2048 x 4096 x 4097 (512 = 3 x 148 + 68 tiles) 2.03 -> 1.9x ms
+        static int tail_pref = -1;     // ADB_GEMM_TAIL=0: off (A/B measurements)
+        if (tail_pref < 0) { const char* e = getenv("ADB_GEMM_TAIL"); tail_pref = (e && e[0] == '0') ? 0 : 1; }
+        const bool big_tail = tail_pref && batch == 1 && big_tiles >= 296 && big_tiles % 148 > 0 && (big_tiles % 148) * 2 <= 148 && K >= 3072;
+        const bool small = !skinny && !skinny_s && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && ((waste_big > 1.05 && !big_tail) || short_k)))));
         const int bm = skinny_s ? CfgSkinnyS::BM : skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM;
         const int bn = skinny_s ? CfgSkinnyS::BN : skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
@@ -597,36 +634,71 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             p.kt_per_split = kt_per_split; p.blocked = blocked;
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
+            p.tile_offset = 0; p.ws_tiles = 0;
+            auto dispatch = [&](const GemmParams& pp, int sp, int ntiles) -> int {
+                if (skinny_s) {
+                    if (a_kc && b_kc) return launch_tma<CfgSkinnyS, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (a_kc && !b_kc) return launch_tma<CfgSkinnyS, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (!a_kc && b_kc) return launch_tma<CfgSkinnyS, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else return launch_tma<CfgSkinnyS, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                } else if (skinny) {
+                    if (a_kc && b_kc) return launch_tma<CfgSkinny, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (a_kc && !b_kc) return launch_tma<CfgSkinny, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (!a_kc && b_kc) return launch_tma<CfgSkinny, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else return launch_tma<CfgSkinny, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                } else if (small) {
+                    if (a_kc && b_kc) return launch_tma<CfgSmall, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (a_kc && !b_kc) return launch_tma<CfgSmall, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (!a_kc && b_kc) return launch_tma<CfgSmall, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else return launch_tma<CfgSmall, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                } else {
+                    if (a_kc && b_kc) return launch_tma<CfgBig, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (a_kc && !b_kc) return launch_tma<CfgBig, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else if (!a_kc && b_kc) return launch_tma<CfgBig, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    else return launch_tma<CfgBig, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                }
+            };
+            // Tail wave.  tiles = w * slots + rem: the last rem tiles would hold the machine for a whole wave while filling
+            // only rem / slots of it.  When rem <= slots / 2 the
+            // full waves run as one data-parallel launch and the tail tiles as a second launch split S = slots / rem ways
+            // along K, each slice writing a dense partial tile; gemm_tail_fixup adds the slices in order (deterministic).
             int rc;
-            if (force_path >= 7 && force_path <= 10 && a_kc && b_kc) {
-                p.tiles_m = (int)((M + 63) / 64); p.tiles_n = (int)((N + 63) / 64);
-                make_tmap(&ta, d->A, K, M, batch, d->a_sm, a_bs, BK, 64);
-                make_tmap(&tb, d->B, K, N, batch, d->b_sn, b_bs, BK, 64);
-                rc = force_path == 7 ? launch_tma<CfgSmallSolo, true, true>(ta, tb, p, (int)batch, splits, st)
-                   : force_path == 8 ? launch_tma<CfgSmall4, true, true>(ta, tb, p, (int)batch, splits, st)
-                   : force_path == 9 ? launch_tma<CfgSmallSync, true, true>(ta, tb, p, (int)batch, splits, st)
-                   : launch_tma<CfgSmallFence, true, true>(ta, tb, p, (int)batch, splits, st);
-            } else if (skinny_s) {
-                if (a_kc && b_kc) rc = launch_tma<CfgSkinnyS, true, true>(ta, tb, p, (int)batch, splits, st);
-                else if (a_kc && !b_kc) rc = launch_tma<CfgSkinnyS, true, false>(ta, tb, p, (int)batch, splits, st);
-                else if (!a_kc && b_kc) rc = launch_tma<CfgSkinnyS, false, true>(ta, tb, p, (int)batch, splits, st);
-                else rc = launch_tma<CfgSkinnyS, false, false>(ta, tb, p, (int)batch, splits, st);
-            } else if (skinny) {
-                if (a_kc && b_kc) rc = launch_tma<CfgSkinny, true, true>(ta, tb, p, (int)batch, splits, st);
-                else if (a_kc && !b_kc) rc = launch_tma<CfgSkinny, true, false>(ta, tb, p, (int)batch, splits, st);
-                else if (!a_kc && b_kc) rc = launch_tma<CfgSkinny, false, true>(ta, tb, p, (int)batch, splits, st);
-                else rc = launch_tma<CfgSkinny, false, false>(ta, tb, p, (int)batch, splits, st);
-            } else if (small) {
-                if (a_kc && b_kc) rc = launch_tma<CfgSmall, true, true>(ta, tb, p, (int)batch, splits, st);
-                else if (a_kc && !b_kc) rc = launch_tma<CfgSmall, true, false>(ta, tb, p, (int)batch, splits, st);
-                else if (!a_kc && b_kc) rc = launch_tma<CfgSmall, false, true>(ta, tb, p, (int)batch, splits, st);
-                else rc = launch_tma<CfgSmall, false, false>(ta, tb, p, (int)batch, splits, st);
-            } else {
-                if (a_kc && b_kc) rc = launch_tma<CfgBig, true, true>(ta, tb, p, (int)batch, splits, st);
-                else if (a_kc && !b_kc) rc = launch_tma<CfgBig, true, false>(ta, tb, p, (int)batch, splits, st);
-                else if (!a_kc && b_kc) rc = launch_tma<CfgBig, false, true>(ta, tb, p, (int)batch, splits, st);
-                else rc = launch_tma<CfgBig, false, false>(ta, tb, p, (int)batch, splits, st);
+            const long long tiles2d = (long long)p.tiles_m * p.tiles_n;
+            const long long full = tiles2d / slots * slots, rem = tiles2d - full;
+            int tail_s = 0;
+            // (measured, profiles/r02_gemm_tail_ab.log: the two extra launches cost ~40 us, so it pays for 128x128 tiles with a long K;
+            // 64x64 tiles lose little to their last wave - its CTAs run alone on their SMs, 1.2x faster - and got slower)
+            if (tail_pref && splits == 1 && batch == 1 && !small && !skinny && !skinny_s && (force_path == 0 || force_path == 4) &&
+                full > 0 && rem > 0 && rem * 2 <= slots && total_kt >= 64) {
+                long long sc = slots / rem;
+                if (sc > 8) sc = 8;
+                if (sc > total_kt / 16) sc = total_kt / 16;
+                if (sc >= 2) tail_s = (int)sc;
             }
+            if (tail_s >= 2) {
+                double* ws_t = nullptr;
+                const int kts = (total_kt + tail_s - 1) / tail_s;
+                const int ns = (total_kt + kts - 1) / kts;
+                cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws_t), (size_t)ns * rem * bm * bn * sizeof(double), st);
+                if (e != cudaSuccess) return set_error("gemm: tail workspace allocation failed: %s", cudaGetErrorString(e));
+                rc = dispatch(p, 1, (int)full);
+                if (rc == 0) {
+                    GemmParams pt = p;
+                    pt.tile_offset = (int)full; pt.ws_tiles = (int)rem; pt.kt_per_split = kts;
+                    pt.C = ws_t; pt.c_sm = bn; pt.c_sn = 1; pt.c_sb = 0; pt.c_ss = 0;
+                    rc = dispatch(pt, ns, (int)rem);
+                }
+                if (rc == 0) {
+                    gemm_tail_fixup<<<(unsigned)rem, 256, 0, st>>>(ws_t, ns, (int)rem, bm, bn, (int)full, p.tiles_m, p.tiles_n, (int)M, (int)N,
+                                                                  d->C, d->c_sm, d->c_sn);
+                    e = cudaGetLastError();
+                    if (e != cudaSuccess) rc = set_error("gemm tail fix-up launch failed: %s", cudaGetErrorString(e));
+                    else count_launch();
+                }
+                cudaFreeAsync(ws_t, st);
+                return rc;
+            }
+            rc = dispatch(p, splits, -1);
             if (rc == 0 && splits > 1) {
                 // C[b][m][n] = sum_z ws[z][b][m][n]  (deterministic order, column-mode reduction kernel)
                 ReduceSpec S;

@@ -135,11 +135,12 @@ def bench_c3(args, dist, timer, ws, rank):
         ms_nocomm = timer.run(lambda: dp.train_step(nn, opt, xd, yd, gbatch, None, read_loss=True), 3, 1)
     t.cuda.synchronize()
     h0 = time.perf_counter()
-    for _ in range(3):
-        dp.train_step(nn, opt, xd, yd, gbatch, dist, read_loss=False)
+    pend = [dp.train_step(nn, opt, xd, yd, gbatch, dist, read_loss="deferred") for _ in range(3)]     # (same graph, loss read later)
     host_ms = (time.perf_counter() - h0) * 1e3 / 3
+    for pl in pend:
+        pl.value()
     t.cuda.synchronize()
-    del nn, opt
+    del nn, opt, pend
     # ---- parity: 9 Adam steps (4 + 5, as the timed run) from the same weights, DP (3 runs) vs single process on the full batch
     nsteps, runs = 9, 3
     dp_losses, dp_w = [], []
@@ -205,7 +206,7 @@ def bench_c4(args, dist, timer, ws, rank, ad):
 
     def c4_step():
         last["loss"], last["grads"] = run(xd, yd, dist)
-    ms = timer.run(c4_step, max(3, min(args.steps, 10)), 3)
+    ms = timer.run(c4_step, max(3, min(args.steps, 10)), 6)       # (6 warm-up steps: deferred gradients + tape + CUDA graph are all live)
     parity = None
     if rank == 0:
         got = [to_host(g) for g in last["grads"]]
@@ -245,6 +246,7 @@ def bench_c5(args, dist, timer, ws, rank, ad, hidden=1024, steps=128, gbatch=512
     def run(rows, d):
         oh = wl._SlicedDevice(to_device(np.eye(vocab)[idx[rows[0]:rows[1]]]))
         def once():
+            info.pop("gg", None)           # (a live value of the previous evaluation would pin the tape's CUDA-graph buffer)
             P = [Variable(p, name="p%d" % i) for i, p in enumerate(prm)]
             t0 = time.perf_counter()
             loss = wl.char_rnn(ad, oh, *P)
@@ -260,7 +262,8 @@ def bench_c5(args, dist, timer, ws, rank, ad, hidden=1024, steps=128, gbatch=512
     t.cuda.synchronize()
     kernels = ad.launch_count() - l0
     first_build = info["build_s"]
-    ms = timer.run(once, 2, 2)               # steady state of a loop that rebuilds the graph every evaluation
+    ms = timer.run(once, 2, 6)               # steady state of a loop that rebuilds the graph every evaluation (deferred gradients,
+                                             # core/grad.py, replay from the 6th evaluation of a structure on)
     s = ms * 1e-3
     parity = None
     if rank == 0:

@@ -657,6 +657,58 @@ def _tape_graphs(ad, seed):
     return out
 
 
+@pytest.fixture
+def plain_grad():
+    """The launch-tape tests count records / replays per structure: keep `ad.grad` on the plain path there (deferred gradients
+    change how many distinct structures a loop goes through; test_deferred_gradients_replay_bitwise covers them)."""
+    from autodiff_b200.core import grad as G
+    saved = G.LAZY
+    G.LAZY = False
+    yield
+    G.LAZY = saved
+
+
+def test_deferred_gradients_replay_bitwise(ad):
+    """Loops that rebuild an isomorphic graph every step: from the 2nd step `ad.grad` returns deferred gradients, and once
+    their structure has a launch tape the evaluation replays it straight from the forward graph's leaves (core/grad.py) -
+    bit for bit the values of the plain path (no tapes, expanded gradient graphs), first and second order, conv included."""
+    from autodiff_b200.core import engine, grad as G, tape
+    if not tape.ENABLED:
+        pytest.skip("ADB_TAPE=0")
+    tape.clear()
+    want = {}
+    tape.ENABLED = False                  # (also keeps ad.grad on the plain path)
+    try:
+        for seed in range(9):
+            for name, nodes in _tape_graphs(ad, seed).items():
+                engine.evaluate_many(nodes)
+                want[(seed, name)] = [np.asarray(n()) for n in nodes]
+    finally:
+        tape.ENABLED = True
+    saved, G.LAZY = G.LAZY, True
+    before = G.stats.get("lazy_replays", 0)
+    try:
+        for seed in range(9):
+            for name, nodes in _tape_graphs(ad, seed).items():
+                engine.evaluate_many(nodes)
+                for k, (n, w) in enumerate(zip(nodes, want[(seed, name)])):
+                    g = np.asarray(n())
+                    assert g.shape == w.shape, (seed, name, k)
+                    assert np.array_equal(g, w), "seed %d graph %s output %d differs with deferred gradients" % (seed, name, k)
+        assert G.stats["deferred"] > 0
+        assert G.stats.get("lazy_replays", 0) - before >= 6, G.stats      # mlp, rnn (2nd order) and conv each reach the lazy replay
+        # a deferred gradient used as an ordinary operand expands and evaluates like the plain graph
+        nodes = _tape_graphs(ad, 50)["mlp"]
+        assert type(nodes[0]) is G.DeferredGrad
+        twice = nodes[0] * 2.0
+        ref = _tape_graphs(ad, 50)["mlp"]
+        assert np.array_equal(np.asarray(twice()), 2.0 * np.asarray(ref[0]()))
+    finally:
+        G.LAZY = saved
+        tape.clear()
+
+
+@pytest.mark.usefixtures("plain_grad")
 def test_launch_tapes_replay_bitwise(ad):
     """From the 3rd evaluation of a structure on, evaluate_many replays a launch tape: results must equal the normal
     planner/executor path bit for bit, for fresh data and fresh graph objects every time."""
@@ -685,6 +737,7 @@ def test_launch_tapes_replay_bitwise(ad):
     assert tape.stats["replays"] - before["replays"] >= 12, tape.stats
 
 
+@pytest.mark.usefixtures("plain_grad")
 def test_launch_tapes_cuda_graph_replay(ad):
     """From the 2nd replay on a small-leaf tape is ONE cudaGraphLaunch (core/tape.py): values equal the planner path bit for
     bit on fresh data; a value of the previous replay that is still alive forces the call-by-call path (and keeps its
@@ -736,6 +789,7 @@ def test_launch_tapes_cuda_graph_replay(ad):
         assert np.array_equal(np.asarray(a()), np.asarray(b()))
 
 
+@pytest.mark.usefixtures("plain_grad")
 def test_launch_tapes_cuda_graph_label_flag(ad):
     from autodiff_b200.core import engine, tape
     if not (tape.ENABLED and tape.GRAPH):
@@ -772,6 +826,7 @@ def test_launch_tapes_cuda_graph_label_flag(ad):
     check(sce(), onp.SoftmaxCEWithLogits(labels=onp.Variable(lab), logits=onp.Variable(np.exp(z * 0.5) + z))())
 
 
+@pytest.mark.usefixtures("plain_grad")
 def test_launch_tapes_intermediates_flags_and_callbacks(ad):
     from autodiff_b200.core import engine, tape
     if not tape.ENABLED:

@@ -235,6 +235,17 @@ int main(int argc, char** argv) {
         }
         return fails ? 1 : 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "tail")) {            // shapes whose last wave is split along K (ADB_GEMM_TAIL=0 turns it off)
+        run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 0}, true, 5);    // C3 forward on a 1024-row shard
+        run_case(Case{1024, 4096, 4096, 1, 1, 1, 0, 0}, true, 5);    // its dX (ragged column cut off by the planner)
+        run_case(Case{4096, 4096, 1024, 1, 0, 0, 0, 0}, true, 5);    // its dW (6.9 waves: no tail)
+        run_case(Case{1000, 3970, 777, 1, 1, 1, 0, 0}, true, 3);     // ragged rows and columns in the tail tiles
+        run_case(Case{1000, 3970, 777, 1, 0, 0, 0, 0}, true, 3);
+        run_case(Case{1280, 2048, 1024, 1, 1, 0, 0, 4}, true, 3);    // 128x128 tiles: 160 = 148 + 12, tail split 8 ways
+        run_case(Case{1281, 2047, 1000, 1, 0, 1, 0, 4}, true, 3);
+        run_case(Case{2048, 4096, 4097, 1, 1, 0, 0, 0}, true, 5);    // 2048-row shard (6.9 waves of small tiles: no tail)
+        return fails ? 1 : 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "shortk")) {          // conv dX: huge M, short K (write-dominated)
         for (int path : {0, 3, 4}) run_case(Case{802816, 400, 32, 1, 1, 1, 0, path}, true, 3);
         for (int path : {0, 3, 4}) run_case(Case{802816, 400, 32, 1, 1, 0, 0, path}, true, 3);
