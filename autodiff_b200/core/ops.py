@@ -17,7 +17,7 @@ from string import ascii_lowercase, ascii_uppercase
 import numpy as np
 
 from .. import _lib
-from ..device import DeviceArray, stream_ptr, torch
+from ..device import DeviceArray, copy_device, fill_device, stream_ptr, to_host, torch
 from . import engine
 from .engine import dev, run_program, scalar_of
 from .fusion import broadcast_shapes
@@ -483,8 +483,7 @@ class SoftmaxCEWithLogits(Node):
     def _eval_device(self):
         lab, z = dev(self.labels), dev(self.logits)
         if z.ndim != 2 or lab.ndim != 2:
-            raise NotImplementedError("SoftmaxCEWithLogits on device supports 2-D labels/logits (the reference checks "
-                                      "labels along axis=1, ops.py:246)")
+            return self._eval_device_nd(lab, z)
         lab = lab.broadcast_to(z.shape)
         out = DeviceArray.empty((z.shape[0],))
         t = torch()
@@ -492,6 +491,43 @@ class SoftmaxCEWithLogits(Node):
         tl, tz, to = lab.tensor(), z.tensor(), out.tensor()
         _lib.call("adb_softmax_ce", C.byref(tl), C.byref(tz), C.byref(to), C.c_void_p(flag.data_ptr()), C.c_void_p(stream_ptr()))
         engine.add_pending_flag(flag, ValueError("Labels must be a valid probability distribution!"))
+        return out
+
+    def _eval_device_nd(self, lab, z):
+        """Labels / logits that are not both 2-D, with the reference's exact semantics (ops.py:243-255): the distribution
+        check sums the labels along axis ONE whatever their rank (so one-hot (B,T,V) labels are rejected, as upstream), the
+        log-sum-exp and the final sum run along the LAST axis, and labels broadcast against logits.  Rare path: the check is
+        read back synchronously; the arithmetic is the 2-D kernel over the flattened leading axes (its own last-axis label
+        check is ignored)."""
+        if lab.ndim < 2:
+            raise np.exceptions.AxisError(1, lab.ndim)                               # np.sum(labels_val, axis=1)
+        red_shape = tuple(1 if i == 1 else d for i, d in enumerate(lab.shape))
+        red = DeviceArray.empty(red_shape)
+        tl, tr = lab.tensor(), red.tensor()
+        _lib.call("adb_reduce_sum", C.byref(tl), C.byref(tr), C.c_void_p(stream_ptr()))
+        sums = to_host(red)
+        if not np.allclose(sums, np.ones_like(sums)):
+            raise ValueError("Labels must be a valid probability distribution!")
+        full = tuple(np.broadcast_shapes(lab.shape, z.shape))
+        rows, cols = int(np.prod(full[:-1], dtype=np.int64)), full[-1]
+
+        def flat(a):
+            a = a.broadcast_to(full)
+            v = a.reshape_view((rows, cols)) if a.is_dense() else None
+            if v is None:
+                d = DeviceArray.empty(full)
+                copy_device(a, d)
+                v = d.reshape_view((rows, cols))
+            return v
+        out = DeviceArray.empty(full[:-1])
+        if rows * cols == 0:
+            if out.size:
+                fill_device(out, 0.0)
+            return out
+        t = torch()
+        flag = t.zeros(1, dtype=t.int32, device="cuda")
+        tl, tz, to = flat(lab).tensor(), flat(z).tensor(), out.reshape_view((rows,)).tensor()
+        _lib.call("adb_softmax_ce", C.byref(tl), C.byref(tz), C.byref(to), C.c_void_p(flag.data_ptr()), C.c_void_p(stream_ptr()))
         return out
 
     def _partial_derivative(self, wrt, previous_grad):

@@ -207,12 +207,22 @@ class Pad(Node):
         self.shape = tuple(d + lo + hi for d, (lo, hi) in zip(self.node.shape, self._pairs))
 
     def _eval_device(self):
+        """np.pad(mode="constant") pads axis by axis, first axis first, each time over the full extent of the array padded so
+        far (numpy lib/arraypad.py `_set_pad_area` loop): where the pad slabs of two axes overlap, the LATER axis' constant
+        wins.  One constant for all sides is a single fill; per-side constants are one fill per non-empty slab in that order."""
         x = dev(self.node)
-        cv = np.unique(np.asarray(self.constant_values, dtype=np.float64))
-        if cv.size != 1:
-            raise NotImplementedError("Pad on device supports one constant value for all sides")
+        nd = len(self.shape)
+        cv = np.broadcast_to(np.asarray(self.constant_values, dtype=np.float64), (nd, 2)) if nd else np.zeros((0, 2))
         out = DeviceArray.empty(self.shape)
-        fill_device(out, float(cv[0]))
+        if np.unique(cv).size <= 1:
+            fill_device(out, float(cv.flat[0]) if cv.size else 0.0)
+        else:
+            for ax, (lo, hi) in enumerate(self._pairs):
+                full = [slice(None)] * nd
+                if lo:
+                    fill_device(out.getitem(tuple(full[:ax] + [slice(0, lo)] + full[ax + 1:])), float(cv[ax, 0]))
+                if hi:
+                    fill_device(out.getitem(tuple(full[:ax] + [slice(self.shape[ax] - hi, None)] + full[ax + 1:])), float(cv[ax, 1]))
         inner = tuple(slice(lo, lo + d) for d, (lo, hi) in zip(x.shape, self._pairs))
         copy_device(x, out.getitem(inner))
         return out

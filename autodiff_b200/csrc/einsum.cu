@@ -9,6 +9,7 @@
 //   no summed letter                      -> ewise product program (broadcast / outer / Hadamard / permute)
 //   2 operands, letters split cleanly into batch | M | N | K groups that each collapse to one stride
 //   and M,N >= 16, K >= 4                -> strided-batched FP64 GEMM (TMA + DMMA)
+//   3+ operands with summed letters, large  -> chain of pairwise contractions (each again one of these forms)
 //   anything else                         -> sum-of-products reduction kernel (row or column mode)
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -343,12 +344,161 @@ static int ragged_edge(const Problem& P, const adb_gemm_desc& d, bool swapped, l
     return best;
 }
 
+static int run_problem(const Problem& P, cudaStream_t st, std::string* desc);
+
+// ---- three or more operands with summed letters: a chain of pairwise contractions ---------------------------------------
+// np.einsum (reference ops.py:180, optimize=False) walks the full iteration space  prod(extent of every letter)  with one
+// multiply per operand; so did the sum-of-products reduction kernel here (on the DFMA pipe).  Contracting two operands at
+// a time - greedily the pair with the smallest iteration space, summing every letter nothing else needs - turns
+// 'ij,jk,kl->il' from I*J*K*L products into two GEMMs on the DMMA pipe, and the gradient of a 3-operand einsum (again a
+// 3-operand einsum, ops.py:182-213) likewise.  Intermediates are dense stream-ordered temporaries laid out
+// [letters of both | letters of the first | letters of the second] so the pair step itself collapses to a GEMM.
+struct PairPlan {
+    int i, j;
+    double iter, inter;          // iteration space of the pair step, elements of its intermediate
+};
+
+static bool pair_letter_kept(const Problem& P, const Letter& l, int i, int j) {
+    if (l.in_out) return true;
+    for (int t = 0; t < P.n_ops; ++t)
+        if (t != i && t != j && l.present[t]) return true;
+    return false;
+}
+
+static PairPlan best_pair(const Problem& P) {
+    PairPlan best{-1, -1, 0, 0};
+    for (int i = 0; i < P.n_ops; ++i)
+        for (int j = i + 1; j < P.n_ops; ++j) {
+            double iter = 1, inter = 1;
+            for (auto& l : P.letters) {
+                if (!l.present[i] && !l.present[j]) continue;
+                iter *= (double)l.extent;
+                if (pair_letter_kept(P, l, i, j)) inter *= (double)l.extent;
+            }
+            if (best.i < 0 || iter < best.iter || (iter == best.iter && inter < best.inter)) best = PairPlan{i, j, iter, inter};
+        }
+    return best;
+}
+
+// Is the chain worth it?  Simulates the greedy order on extents only.
+static bool pairwise_pays(const Problem& P0) {
+    static int pref = -1;                // ADB_EINSUM_PAIRWISE=0: off (A/B measurements)
+    if (pref < 0) { const char* e = getenv("ADB_EINSUM_PAIRWISE"); pref = (e && e[0] == '0') ? 0 : 1; }
+    if (!pref) return false;
+    double naive = 1, biggest = 1;
+    for (auto& l : P0.letters) naive *= (double)l.extent;
+    for (int t = 0; t <= P0.n_ops; ++t) {                       // largest operand / the output
+        double e = 1;
+        for (auto& l : P0.letters) if (t < P0.n_ops ? l.present[t] : l.in_out) e *= (double)l.extent;
+        biggest = std::max(biggest, e);
+    }
+    if (P0.n_ops > ADB_RED_MAX_OPS) return true;                // the reduction kernel cannot take it at all
+    if (naive * P0.n_ops < 4.0e6) return false;                 // one small launch beats a chain of launches
+    Problem P = P0;
+    double chain = 0;
+    while (P.n_ops > 2) {
+        const PairPlan pp = best_pair(P);
+        chain += pp.iter;
+        if (pp.inter > 4.0 * biggest && pp.inter * 8.0 > 256e6) return false;      // an outer-product blow-up: stay fused
+        std::vector<Letter> keep;
+        for (auto& l : P.letters) {
+            const bool in_pair = l.present[pp.i] || l.present[pp.j];
+            if (in_pair && !pair_letter_kept(P, l, pp.i, pp.j)) continue;
+            Letter n = l;
+            n.present[pp.i] = in_pair;
+            for (int t = pp.j; t + 1 < P.n_ops; ++t) n.present[t] = n.present[t + 1];
+            keep.push_back(n);
+        }
+        P.letters = keep;
+        --P.n_ops;
+    }
+    double last = 1;
+    for (auto& l : P.letters) last *= (double)l.extent;
+    chain += last;
+    return chain * 2.0 <= naive;
+}
+
+static int run_pairwise(const Problem& P0, cudaStream_t st, std::string* desc) {
+    Problem P = P0;
+    std::vector<double*> temps;
+    std::string text = "pairwise[";
+    int rc = 0;
+    while (P.n_ops > 2 && rc == 0) {
+        const PairPlan pp = best_pair(P);
+        const int i = pp.i, j = pp.j;
+        Problem S;
+        S.n_ops = 2;
+        S.op[0] = P.op[i]; S.op[1] = P.op[j];
+        S.empty_out = S.empty_sum = false;
+        std::vector<int> src;                                    // index into P.letters of every letter of S
+        for (int k = 0; k < (int)P.letters.size(); ++k) {
+            const Letter& l = P.letters[k];
+            if (!l.present[i] && !l.present[j]) continue;
+            Letter n;
+            memset(&n, 0, sizeof n);
+            n.c = l.c; n.extent = l.extent;
+            n.s[0] = l.s[i]; n.present[0] = l.present[i];
+            n.s[1] = l.s[j]; n.present[1] = l.present[j];
+            n.in_out = pair_letter_kept(P, l, i, j);
+            S.letters.push_back(n);
+            src.push_back(k);
+        }
+        // dense layout of the intermediate: [both | first only | second only], each group in its source's stride order
+        std::vector<int> order;
+        for (int k = 0; k < (int)S.letters.size(); ++k) if (S.letters[k].in_out) order.push_back(k);
+        if ((int)order.size() > ADB_MAX_RANK) { rc = set_error("einsum: intermediate of rank %d (max %d)", (int)order.size(), ADB_MAX_RANK); break; }
+        auto grp = [&](int k) { const Letter& l = S.letters[k]; return l.present[0] && l.present[1] ? 0 : (l.present[0] ? 1 : 2); };
+        auto key = [&](int k) { const Letter& l = S.letters[k]; const long long v = grp(k) == 2 ? l.s[1] : l.s[0]; return v < 0 ? -v : v; };
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return grp(a) != grp(b) ? grp(a) < grp(b) : key(a) > key(b); });
+        long long elems = 1;
+        for (int r = (int)order.size() - 1; r >= 0; --r) { S.letters[order[r]].os = elems; elems *= S.letters[order[r]].extent; }
+        double* tmp = nullptr;
+        if (!desc) {
+            cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)std::max(elems, 1LL) * sizeof(double), st);
+            if (e != cudaSuccess) { rc = set_error("einsum: intermediate allocation failed: %s", cudaGetErrorString(e)); break; }
+            temps.push_back(tmp);
+        }
+        S.out = tmp;
+        S.out_t.ptr = tmp; S.out_t.rank = (int)order.size();
+        for (int r = 0; r < (int)order.size(); ++r) { S.out_t.shape[r] = S.letters[order[r]].extent; S.out_t.stride[r] = S.letters[order[r]].os; }
+        std::string sub;
+        rc = run_problem(S, st, desc ? &sub : nullptr);
+        if (desc) text += (text.size() > 9 ? " ; " : "") + sub;
+        // the pair becomes one operand (slot i); slot j closes up
+        std::vector<Letter> keep;
+        for (int k = 0; k < (int)P.letters.size(); ++k) {
+            Letter n = P.letters[k];
+            const auto it = std::find(src.begin(), src.end(), k);
+            if (it != src.end()) {
+                const Letter& sl = S.letters[it - src.begin()];
+                if (!sl.in_out) continue;                        // summed by this step
+                n.s[i] = sl.os; n.present[i] = true;
+            }
+            for (int t = j; t + 1 < P.n_ops; ++t) { n.s[t] = n.s[t + 1]; n.present[t] = n.present[t + 1]; }
+            n.s[P.n_ops - 1] = 0; n.present[P.n_ops - 1] = false;
+            keep.push_back(n);
+        }
+        P.letters = keep;
+        P.op[i] = tmp;
+        for (int t = j; t + 1 < P.n_ops; ++t) P.op[t] = P.op[t + 1];
+        --P.n_ops;
+    }
+    if (rc == 0) {
+        std::string sub;
+        rc = run_problem(P, st, desc ? &sub : nullptr);
+        if (desc) *desc = text + " ; " + sub + "]";
+    }
+    for (double* t : temps) cudaFreeAsync(t, st);
+    return rc;
+}
+
 static int run_problem(const Problem& P, cudaStream_t st, std::string* desc) {
     if (P.empty_out) { if (desc) *desc = "empty"; return 0; }
     if (P.empty_sum) return run_fill_zero(P, st, desc);
     bool has_sum = false;
     for (auto& l : P.letters) has_sum |= !l.in_out;
     if (!has_sum) return run_product(P, st, desc);
+    if (P.n_ops >= 3 && pairwise_pays(P)) return run_pairwise(P, st, desc);
     adb_gemm_desc d;
     memset(&d, 0, sizeof d);
     bool swapped = false;

@@ -50,8 +50,17 @@ struct TileCfg {
     static constexpr int PREFETCH = PREFETCH_;
     static constexpr int SMEM = STAGES_ * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES_ * 8;
 };
-using CfgBig = TileCfg<128, 128, 6, 1>;
-using CfgSmall = TileCfg<64, 64, 6, 2>;
+#ifndef ADB_BIG_STAGES          // (compile-time knobs for the A/B builds of tools/gemm_variants.sh)
+#define ADB_BIG_STAGES 6
+#endif
+#ifndef ADB_BIG_PREFETCH
+#define ADB_BIG_PREFETCH (ADB_BIG_STAGES - 2)
+#endif
+#ifndef ADB_SMALL_PREFETCH
+#define ADB_SMALL_PREFETCH 4
+#endif
+using CfgBig = TileCfg<128, 128, ADB_BIG_STAGES, 1, 2, 4, ADB_BIG_PREFETCH>;
+using CfgSmall = TileCfg<64, 64, 6, 2, 2, 4, ADB_SMALL_PREFETCH>;
 // Tall-and-skinny problems (im2col convolutions: M = batch*OH*OW, N = output channels <= 32): all 8 warps stack along M
 // and share the whole 32-column B tile, so no MMA work is spent on padding columns.
 using CfgSkinny = TileCfg<256, 32, 6, 1, 8, 1>;

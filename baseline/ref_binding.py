@@ -84,7 +84,7 @@ class Dev:
 
     @staticmethod
     def upload(a):
-        a = np.ascontiguousarray(a, dtype=np.float64)
+        a = np.asarray(a, dtype=np.float64, order="C")           # (np.ascontiguousarray would turn a 0-d value into shape (1,))
         d = Dev(a.shape)
         if a.size:
             check(lib().adb_memcpy_h2d(d.ptr, a.ctypes.data_as(C.c_void_p), a.nbytes, None))

@@ -971,3 +971,49 @@ def test_baseline_size_contractions_vs_blas(ad):
     assert outer.shape == (128, 128, 128, 128)
     assert np.array_equal(outer[5, :, 7, :], g2[5, 7] * m2) and np.array_equal(outer[:, 100, :, 3], g2 * m2[100, 3])
     assert abs(outer.sum() - g2.sum() * m2.sum()) <= 1e-9 * abs(g2.sum() * m2.sum()) + 1e-6
+
+
+def test_pad_per_side_constants(ad):
+    """np.pad(mode="constant") with a different constant per side (reference reshape.py:124-129 hands constant_values to
+    np.pad unchanged): overlapping corners take the LATER axis' constant."""
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((5, 7)); x3 = rng.standard_normal((3, 4, 5))
+    for arr, pw, cv in [(x, [[1, 2], [3, 1]], [[1.5, -2.0], [3.0, 4.0]]), (x, [[2, 0], [0, 3]], [0.25, -0.5]),
+                        (x, [[1, 1], [2, 2]], [[7.0], [9.0]]), (x3, [[1, 0], [2, 1], [0, 2]], [[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]),
+                        (x3, 1, [[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]), (x, [[0, 0], [0, 0]], [[1.0, 2.0], [3.0, 4.0]])]:
+        got = ad.Pad(ad.Variable(arr, name="x"), pw, constant_values=cv)
+        ref = np.pad(arr, pw, mode="constant", constant_values=cv)
+        assert tuple(got.shape) == ref.shape
+        assert np.array_equal(got(), ref), (pw, cv)
+        w = ad.Variable(arr, name="x")                                   # gradient: the inner window of the incoming gradient
+        g = ad.grad(ad.Pad(w, pw, constant_values=cv) * 2.0, [w])[0]
+        assert np.array_equal(g(), np.full(arr.shape, 2.0))
+
+
+def test_softmax_ce_nd_reference_semantics(ad):
+    """Labels / logits that are not both 2-D: the reference sums the labels along axis 1 for its distribution check and runs the
+    log-sum-exp along the last axis (ops.py:243-255) - restated by the oracle, matched here."""
+    rng = np.random.default_rng(22)
+    z = rng.standard_normal((6, 5, 9)) * 3
+    lab = rng.random((6, 5, 9)); lab /= lab.sum(1, keepdims=True)        # a distribution along axis ONE (what upstream checks)
+    got = ad.SoftmaxCEWithLogits(labels=ad.Variable(lab, name="l"), logits=ad.Variable(z, name="z"))
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))
+    assert tuple(got.shape) == tuple(ref.shape) == (6, 5)
+    check(got(), ref())
+    onehot = np.eye(9)[rng.integers(0, 9, (6, 5))]                       # one-hot along the LAST axis: rejected upstream, and here
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        onp.SoftmaxCEWithLogits(labels=onp.Variable(onehot, name="l"), logits=onp.Variable(z, name="z"))()
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        ad.SoftmaxCEWithLogits(labels=ad.Variable(onehot, name="l"), logits=ad.Variable(z, name="z"))()
+    zt = np.ascontiguousarray(z.transpose(1, 0, 2))
+    for m in (ad, onp):                                                   # 1-D labels: np.sum(axis=1) raises AxisError upstream
+        with pytest.raises(np.exceptions.AxisError):
+            m.SoftmaxCEWithLogits(labels=m.Variable(np.full(9, 1 / 9), name="l1"), logits=m.Variable(zt, name="z"))()
+    lab3 = np.ones((5, 1, 9))        # labels that BROADCAST against the logits; axis 1 has one entry, so the check wants all ones
+    vals = []
+    for m in (ad, onp):
+        Z = m.Variable(zt, name="z")
+        e = m.SoftmaxCEWithLogits(labels=m.Variable(lab3, name="l"), logits=Z)
+        g = m.grad(e, [Z])[0]
+        vals.append((np.asarray(e()), np.asarray(g())))
+    check(vals[0][0], vals[1][0]); check(vals[0][1], vals[1][1])
