@@ -1017,3 +1017,57 @@ def test_softmax_ce_nd_reference_semantics(ad):
         g = m.grad(e, [Z])[0]
         vals.append((np.asarray(e()), np.asarray(g())))
     check(vals[0][0], vals[1][0]); check(vals[0][1], vals[1][1])
+
+
+PAIRWISE = [
+    # (sizes bounded by the ORACLE: np.einsum without optimize walks the whole iteration space - 5 operands of ~80 took minutes)
+    ("ij,jk,kl->il", [(120, 100), (100, 110), (110, 90)], None),
+    ("ij,jk,kl->li", [(120, 100), (100, 110), (110, 90)], [(1, 0), None, (1, 0)]),           # transposed (strided) operands
+    ("ab,bc,cd,de,ef->af", [(12, 14), (14, 16), (16, 18), (18, 20), (20, 22)], None),        # more operands than the fused kernel takes
+    ("bij,bjk,bkl->bil", [(6, 64, 80), (6, 80, 96), (6, 96, 72)], None),
+    ("dt,tp,pr->dtp", [(60, 80), (80, 70), (70, 50)], None),                                 # reference tests/test_einsum.py:83-111
+    ("ij,jk,ik->", [(257, 130), (130, 99), (257, 99)], None),
+    ("ij,j,jk->ik", [(150, 333), (333,), (333, 140)], None),
+    ("iij,jk,kl->il", [(90, 90, 70), (70, 110), (110, 50)], None),                           # a diagonal inside a chain
+]
+
+
+@pytest.mark.parametrize("spec,shapes,perms", PAIRWISE)
+def test_einsum_pairwise_chain_forward_and_grads(spec, shapes, perms, ad):
+    """3+ operand contractions run as a chain of pairwise GEMMs (csrc/einsum.cu run_pairwise); values and the gradients w.r.t.
+    every operand (each again a 3+ operand einsum, reference ops.py:182-213) against the numpy oracle."""
+    rng = np.random.default_rng(31)
+    vals = []
+    for k, shp in enumerate(shapes):
+        pm = perms[k] if perms is not None else None
+        if pm is None:
+            vals.append(rng.standard_normal(shp))
+        else:                                                   # a view whose memory order is the permuted one
+            base = rng.standard_normal(tuple(shp[a] for a in pm))
+            vals.append(base.transpose(np.argsort(pm)))
+    outs = {}
+    for mod in (onp, ad):
+        vs = [mod.Variable(v, name="v%d" % i) for i, v in enumerate(vals)]
+        e = mod.Einsum(spec, *vs)
+        outs[mod] = [np.array(e())]
+        if "ii" not in spec:
+            outs[mod] += [np.array(x()) for x in mod.grad(e, vs)]
+    for a, b in zip(outs[ad], outs[onp]):
+        check(a, b, what=spec)
+
+
+def test_einsum_pairwise_chain_beyond_the_oracle(ad):
+    """Five operands of ~80-100: np.einsum (the reference's evaluator, optimize=False) needs minutes for the 3e11-term iteration
+    space, so the check here is the matrix-product chain in numpy BLAS; the planner runs four small GEMMs."""
+    rng = np.random.default_rng(32)
+    shapes = [(64, 80), (80, 96), (96, 72), (72, 88), (88, 100)]
+    vals = [rng.standard_normal(s) for s in shapes]
+    vs = [ad.Variable(v, name="v%d" % i) for i, v in enumerate(vals)]
+    e = ad.Einsum("ab,bc,cd,de,ef->af", *vs)
+    a, b, c, d, f = vals
+    check(e(), a @ b @ c @ d @ f, what="chain")
+    g = ad.grad(e, vs)
+    ones = np.ones((64, 100))
+    check(g[0](), ones @ (b @ c @ d @ f).T, what="d/da")
+    check(g[2](), (a @ b).T @ ones @ (d @ f).T, what="d/dc")
+    check(g[4](), (a @ b @ c @ d).T @ ones, what="d/df")

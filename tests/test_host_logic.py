@@ -165,6 +165,25 @@ def test_planner_classification():
     assert _describe("dt,tp->d", [(2, 3), (3, 5)], (2,)).startswith("reduce")     # 'p' summed out of one operand only
 
 
+def test_planner_pairwise_chain():
+    """3+ operands with summed letters and enough work: a chain of pairwise contractions (GEMMs where the pair collapses)."""
+    d = _describe("ij,jk,kl->il", [(300, 200), (200, 250), (250, 180)], (300, 180))
+    assert d.startswith("pairwise[gemm ") and d.count("gemm M=") == 2, d
+    # gradient of the middle operand (reference ops.py:182-213 swaps the output with the operand): still two GEMMs
+    d = _describe("ij,kl,il->jk", [(300, 200), (250, 180), (300, 180)], (200, 250))
+    assert d.startswith("pairwise[") and d.count("gemm M=") == 2, d
+    d = _describe("ab,bc,cd,de,ef->af", [(64, 80), (80, 96), (96, 72), (72, 88), (88, 100)], (64, 100))     # > ADB_RED_MAX_OPS operands
+    assert d.startswith("pairwise[") and d.count(" ; ") == 3, d
+    d = _describe("bij,bjk,bkl->bil", [(6, 64, 80), (6, 80, 96), (6, 96, 72)], (6, 64, 72))
+    assert d.count("batch=6") == 2, d
+    # 'r' is summed out of one operand alone: that pair step is a reduction, the rest a product
+    d = _describe("dt,tp,pr->dtp", [(200, 300), (300, 250), (250, 150)], (200, 300, 250))
+    assert d.startswith("pairwise[reduce"), d
+    # tiny problems stay one fused launch; so does a chain whose intermediate would be an outer-product blow-up
+    assert _describe("ij,jk,kl->il", [(8, 9), (9, 10), (10, 11)], (8, 11)).startswith("reduce ops=3")
+    assert _describe("ia,ib,ic->abc", [(4, 500), (4, 500), (4, 500)], (500, 500, 500)).startswith("reduce ops=3")
+
+
 def test_planner_errors():
     with pytest.raises(ValueError, match="explicit '->'"):
         _describe("ij,jk", [(2, 3), (3, 4)], (2, 4))
