@@ -67,6 +67,8 @@ PROTOTYPES = {
     "adb_softmax_ce": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "adb_im2col": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
     "adb_col2im": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.c_void_p]),
+    "adb_conv_gemm": (C.c_int, [C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
+    "adb_conv_gemm_ok": (C.c_int, [C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor)]),
     "adb_graph_begin": (C.c_int, [C.c_void_p]),
     "adb_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "adb_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -3,6 +3,7 @@
 Replaces the recursive `child()` calls inside every reference `_eval` (e.g. autodiff/core/ops.py:173) — same
 memoisation contract as reference node.py:42-46, no recursion limit, values stay in HBM between nodes."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -13,6 +14,7 @@ from .node import ConstFill, Node, Variable
 from .utils import gc_paused
 
 fusion_enabled = True   # set False to run one kernel per node (debugging / A-B measurements)
+implicit_conv_enabled = os.environ.get("ADB_IMPLICIT_CONV", "1") != "0"   # Im2Col / Col2Im read through by their einsums (core/conv.py)
 kernel_timings = None   # bench.py sets this to a list; Einsum then records (description, start, stop) CUDA events
 _pending_flags = []   # (torch int32 tensor, exception) raised at the next host synchronisation
 
@@ -42,11 +44,13 @@ def scalar_of(node):
 
 
 class _Plan:
-    __slots__ = ("groups", "absorbed")
+    __slots__ = ("groups", "absorbed", "virtual")
 
     def __init__(self):
         self.groups = {}      # id(root) -> {id(member): member}
         self.absorbed = {}    # id(member) -> root
+        self.virtual = {}     # id(node) -> node that is never materialised: its consumers read THROUGH it (core/conv.py:
+                              # an Im2Col feeding einsums, the einsum feeding a Col2Im - implicit-GEMM convolution)
 
 
 def _plan(tops):
@@ -73,6 +77,9 @@ def _plan(tops):
             consumers.setdefault(id(c), []).append(node)
             if id(c) not in seen:
                 stack.append((c, False))
+    if implicit_conv_enabled:
+        from . import conv as _conv
+        _conv.mark_virtual(order, consumers, top_ids, plan.virtual)
     if not fusion_enabled:
         return plan
     for node in reversed(order):          # consumers before producers
@@ -116,6 +123,22 @@ def _group_inputs(members):
     return deps
 
 
+def _pending(node, plan):
+    """Children `node` needs evaluated first; a virtual child is looked through to its own children."""
+    out = []
+    todo = list(node.children)
+    virtual = plan.virtual
+    while todo:
+        c = todo.pop(0)
+        if _has_value(c) or scalar_of(c) is not None:
+            continue
+        if id(c) in virtual:
+            todo = list(c.children) + todo
+        else:
+            out.append(c)
+    return out
+
+
 def _execute(top, plan):
     from . import fusion
     stack = [top]
@@ -132,6 +155,8 @@ def _execute(top, plan):
         members = plan.groups.get(id(node))
         if members is not None:
             pending = _group_inputs(members)
+        elif plan.virtual:
+            pending = _pending(node, plan)
         else:
             pending = [c for c in node.children if not _has_value(c) and scalar_of(c) is None]
         if pending:
@@ -168,7 +193,7 @@ def evaluate_many(tops, on_ready=None):
     with gc_paused():
         rec, sig, scanned = None, None, None
         if tape.ENABLED and kernel_timings is None and tape._recorder is None:
-            flags = (fusion_enabled, Node.epsilon, len(tops), _device.kernel_mode[0], _device.kernel_mode[1])
+            flags = (fusion_enabled, Node.epsilon, len(tops), _device.kernel_mode[0], _device.kernel_mode[1], implicit_conv_enabled)
             lazy = None
             if _grad_mod is not None and _grad_mod.LAZY:
                 # outputs that are still-deferred gradients (core/grad.py): replay their tape from the forward graph's leaves

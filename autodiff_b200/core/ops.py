@@ -365,6 +365,11 @@ class Einsum(Node):
 
     # ---- device evaluation
     def _eval_device(self):
+        if len(self.children) == 2 and (self.children[0]._dev is None or self.children[1]._dev is None):
+            from . import conv as _conv          # an operand without a value: an Im2Col the plan made virtual (core/conv.py)
+            got = _conv.implicit_einsum(self)
+            if got is not None:
+                return got
         subs = list(self.opnames[:-1])
         out_sub = self.opnames[-1]
         arrs = []

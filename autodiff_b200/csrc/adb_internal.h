@@ -10,6 +10,12 @@ int set_error(const char* fmt, ...);   // stores a thread-local message, returns
 void count_launch(int n = 1);
 int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path);
 int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st);
+// implicit-GEMM convolution (gemm_f64.cu): the im2col matrix of `img` (N,H,W,C) is read through an im2col-mode tensor map
+bool conv_image_ok(const adb_tensor* img, int kh, int kw, int pad_h, int pad_w);
+int conv_gemm_cols(const adb_tensor* img, int kh, int kw, int pad_h, int pad_w, const double* B, long long b_sk, long long b_sn, long long Nn,
+                   double* out, long long c_sm, long long c_sn, cudaStream_t st);
+int conv_gemm_wgrad(const adb_tensor* img, int kh, int kw, const double* D, long long d_sp, long long d_so, long long O,
+                    double* out, long long c_sm, long long c_sn, cudaStream_t st);
 extern int g_precision;   // 0 = FP64 DMMA, 1 = 3xTF32 tcgen05
 int ewise_run(const adb_ew_instr* code, int n_instr, int n_in, const adb_tensor* ins, int n_out, const adb_tensor* outs,
               cudaStream_t st);

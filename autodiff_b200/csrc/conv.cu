@@ -122,4 +122,80 @@ int adb_col2im(const adb_tensor* cols, int kh, int kw, const adb_tensor* dx, voi
     return 0;
 }
 
+// ---- implicit-GEMM convolution: the three contractions around Im2Col / Col2Im without the materialised matrix ----------
+// mode 0  out (P, O)          = Im2Col(x) @ w              x: (N,H,W,C), w: (kh*kw*C, O), P = N*OH*OW        [forward]
+// mode 1  out (kh*kw*C, O)    = Im2Col(x)^T @ d            d: (P, O)                                            [filter gradient]
+// mode 2  out (N,H,W,C)       = Col2Im(d @ w^T)            x := d seen as (N,OH,OW,O), w: (kh*kw*C, O)          [data gradient]
+static int conv_gemm_check(int mode, const adb_tensor* x, int kh, int kw, const adb_tensor* w, const adb_tensor* out, bool quiet) {
+    auto fail = [&](const char* why) { return quiet ? 1 : adb::set_error("conv_gemm: %s", why); };
+    if (mode < 0 || mode > 2) return fail("mode must be 0, 1 or 2");
+    if (x->rank != 4 || w->rank != 2) return fail("x must be 4-D (NHWC) and w / d 2-D");
+    if (kh < 1 || kw < 1) return fail("bad window");
+    const long long N = x->shape[0], H = x->shape[1], W = x->shape[2], C = x->shape[3];
+    auto matrix_ok = [&](const adb_tensor* t) {
+        if ((reinterpret_cast<uintptr_t>(t->ptr) & 15) != 0) return false;
+        if (t->stride[1] == 1) return t->stride[0] > 0 && (t->stride[0] & 1) == 0;
+        return t->stride[0] == 1 && t->stride[1] > 0 && (t->stride[1] & 1) == 0;
+    };
+    if (mode == 2) {
+        // x is dOut (N,OH,OW,O); out is the image gradient (N, OH+kh-1, OW+kw-1, C)
+        if (out->rank != 4) return fail("mode 2: out must be 4-D");
+        const long long Hi = H + kh - 1, Wi = W + kw - 1, Ci = out->shape[3];
+        if (out->shape[0] != N || out->shape[1] != Hi || out->shape[2] != Wi) return fail("mode 2: out has the wrong shape");
+        if (w->shape[0] != (long long)kh * kw * Ci || w->shape[1] != C) return fail("mode 2: w has the wrong shape");
+        if (out->stride[3] != 1 || out->stride[1] != Wi * out->stride[2] || out->stride[0] != Hi * out->stride[1] || out->stride[2] < Ci)
+            return fail("mode 2: out must be a dense NHWC array");
+        if (!adb::conv_image_ok(x, kh, kw, kh - 1, kw - 1)) return fail("mode 2: output gradient not describable by an im2col tensor map");
+        if (Ci > 1024) return fail("mode 2: too many channels");
+        return 0;
+    }
+    const long long OH = H - kh + 1, OW = W - kw + 1;
+    if (OH < 1 || OW < 1) return fail("window larger than the image");
+    if (!adb::conv_image_ok(x, kh, kw, 0, 0)) return fail("image not describable by an im2col tensor map (C % 16, alignment)");
+    if (out->rank != 2) return fail("out must be 2-D");
+    if (mode == 0) {
+        if (w->shape[0] != (long long)kh * kw * C || out->shape[0] != N * OH * OW || out->shape[1] != w->shape[1]) return fail("mode 0: shapes do not match");
+        if (!matrix_ok(w)) return fail("mode 0: w not describable by a tensor map");
+    } else {
+        if (w->shape[0] != N * OH * OW || out->shape[0] != (long long)kh * kw * C || out->shape[1] != w->shape[1]) return fail("mode 1: shapes do not match");
+        if (!matrix_ok(w)) return fail("mode 1: d not describable by a tensor map");
+        if ((long long)kh * kw * C * w->shape[1] > (1LL << 24)) return fail("mode 1: filter too large for the split-K workspace");
+    }
+    return 0;
+}
+
+int adb_conv_gemm_ok(int mode, const adb_tensor* x, int kh, int kw, const adb_tensor* w, const adb_tensor* out) {
+    return conv_gemm_check(mode, x, kh, kw, w, out, true) == 0 ? 1 : 0;
+}
+
+int adb_conv_gemm(int mode, const adb_tensor* x, int kh, int kw, const adb_tensor* w, const adb_tensor* out, void* stream) {
+    if (int rc = conv_gemm_check(mode, x, kh, kw, w, out, false)) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (mode == 0)
+        return adb::conv_gemm_cols(x, kh, kw, 0, 0, w->ptr, w->stride[0], w->stride[1], w->shape[1], out->ptr, out->stride[0], out->stride[1], st);
+    if (mode == 1)
+        return adb::conv_gemm_wgrad(x, kh, kw, w->ptr, w->stride[0], w->stride[1], w->shape[1], out->ptr, out->stride[0], out->stride[1], st);
+    // mode 2: dx[n,y,x,c] = sum_{a,b,o} d[n, y-a, x-b, o] * w[(a,b,c), o]  =  a FULL convolution of d (zero padding k-1) with the
+    // flipped filter  wf[(a',b',o), c] = w[(kh-1-a', kw-1-b', c), o]  (built here: kh*kw*O*C elements, a strided copy)
+    const long long O = x->shape[3], Ci = out->shape[3];
+    double* wf = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wf), (size_t)kh * kw * O * Ci * sizeof(double), st);
+    if (e != cudaSuccess) return adb::set_error("conv_gemm: flipped-filter allocation failed: %s", cudaGetErrorString(e));
+    adb_tensor in, o4;
+    in.rank = o4.rank = 4;
+    const long long r = w->stride[0], c = w->stride[1];
+    in.ptr = w->ptr + ((long long)(kh - 1) * kw + (kw - 1)) * Ci * r;
+    const long long shp[4] = {kh, kw, O, Ci};
+    const long long ist[4] = {-(long long)kw * Ci * r, -Ci * r, c, r};
+    const long long ost[4] = {(long long)kw * O * Ci, O * Ci, Ci, 1};
+    for (int k = 0; k < 4; ++k) { in.shape[k] = o4.shape[k] = shp[k]; in.stride[k] = ist[k]; o4.stride[k] = ost[k]; }
+    o4.ptr = wf;
+    adb_ew_instr code[2] = {{ADB_EW_LOAD | ADB_EW_SRC_IN, 0, 0.0}, {ADB_EW_STORE_OUT, 0, 0.0}};
+    int rc = adb::ewise_run(code, 2, 1, &in, 1, &o4, st);
+    if (rc == 0)
+        rc = adb::conv_gemm_cols(x, kh, kw, kh - 1, kw - 1, wf, Ci, 1, Ci, out->ptr, out->stride[2], 1, st);
+    cudaFreeAsync(wf, st);
+    return rc;
+}
+
 }  // extern "C"

@@ -67,6 +67,8 @@ using CfgSkinny = TileCfg<256, 32, 6, 1, 8, 1>;
 // Few rows AND few columns with a long K (weight gradients of the first conv layer: 75 x 16 x 921600): 128x32 tiles,
 // two CTAs per SM, split-K supplies the parallelism.
 using CfgSkinnyS = TileCfg<128, 32, 6, 2, 8, 1>;
+// Implicit-GEMM convolution onto <= 16 output channels (the data gradient of a conv layer with 16 input channels).
+using CfgSkinny16 = TileCfg<256, 16, 6, 1, 8, 1>;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = CONSUMER_WARPS * 32;   // 9 warps would round to 12 for register allocation (168 regs)
 
@@ -111,6 +113,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// TMA im2col mode (tensor (C, W, H, N)): `pixels` consecutive positions of the bounding box starting at (w, h, n), each read at
+// (w + off_w, h + off_h), 16 channels from c on - one 128-byte row per position (semantics pinned by tools/probe_im2col.cu,
+// profiles/r02_probe_im2col.log: wraps W -> H -> N inside the box, zero-fills outside the tensor).
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n, int off_w, int off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
+        : "memory");
+}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
@@ -127,10 +138,17 @@ struct GemmParams {
     long long c_sm, c_sn, c_sb, c_ss;   // c_ss: stride between split-K partial results
     int tile_offset;             // first tile (raster order) of this launch: the tail wave is a launch of its own
     int ws_tiles;                // > 0: C is a workspace of [gridDim.z][ws_tiles] dense BM x BN tiles (tail wave, see gemm_tail_fixup)
+    // implicit-GEMM convolution (CONV kernels): operand A is never materialised, tmA is an im2col-mode tensor map of the image
+    int cv_wb, cv_hb;            // positions per row / rows per image of the bounding box the windows slide over
+    int cv_lw, cv_lh;            // its lower corner (0 for a VALID convolution, -(k-1) for the data gradient's full convolution)
+    int cv_kw, cv_cpt;           // taps per filter row; k-tiles (16 channels) per tap
 };
 
 // ----------------------------------------------------------------------------- TMA + DMMA kernel
-template <class Cfg, bool A_KC, bool B_KC>
+// CONV = 1: A is the im2col matrix of an NHWC image, read straight from the image by im2col-mode TMA:
+//   A_KC  (forward / data gradient): rows = window positions, k = (tap, channel): one BM-position column per k-tile;
+//   !A_KC (weight gradient):         k = window positions, m = (tap, channel): BM/16 blocks of [16 positions][16 channels].
+template <class Cfg, bool A_KC, bool B_KC, int CONV = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
@@ -170,16 +188,45 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
 
     // ===== TMA producer: lane 0 of warp 0 keeps PREFETCH k-tiles in flight (issued between its own MMAs) =====
+    int cv_n = 0, cv_h = 0, cv_w = 0, cv_blocks = BM / 16;
+    if (CONV && threadIdx.x == 0) {
+        if (A_KC) {                                    // first window position of this row tile
+            const int per_img = p.cv_hb * p.cv_wb;
+            cv_n = m0 / per_img;
+            const int r = m0 - cv_n * per_img;
+            cv_h = r / p.cv_wb;
+            cv_w = r - cv_h * p.cv_wb;
+        } else {                                       // (tap, channel-chunk) blocks of this tile that exist
+            const int left = (p.M - m0 + 15) / 16;
+            cv_blocks = left < BM / 16 ? left : BM / 16;
+        }
+    }
     auto issue_tile = [&](int kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t fb = full0 + 8 * s;
-        mbar_expect_tx(fb, STAGE_BYTES);
+        mbar_expect_tx(fb, (CONV && !A_KC) ? cv_blocks * 2048 + Cfg::B_TILE_BYTES : STAGE_BYTES);
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + A_TILE_BYTES;
         const int k0 = (kt_first + kt) * BK;
-        if (A_KC) {
+        if (CONV && A_KC) {
+            const int kk = kt_first + kt;
+            const int tap = kk / p.cv_cpt, c0 = (kk - tap * p.cv_cpt) * 16;
+            const int ta = tap / p.cv_kw, tb = tap - ta * p.cv_kw;
+            tma_load_im2col(sa, &tmA, fb, c0, cv_w + p.cv_lw, cv_h + p.cv_lh, cv_n, tb, ta);
+        } else if (CONV) {
+            const int per_img = p.cv_hb * p.cv_wb;
+            const int n = k0 / per_img;
+            const int r = k0 - n * per_img;
+            const int h = r / p.cv_wb, w = r - h * p.cv_wb;
+            for (int b = 0; b < cv_blocks; ++b) {
+                const int blk = m0 / 16 + b;
+                const int tap = blk / p.cv_cpt, c0 = (blk - tap * p.cv_cpt) * 16;
+                const int ta = tap / p.cv_kw, tb = tap - ta * p.cv_kw;
+                tma_load_im2col(sa + b * 2048, &tmA, fb, c0, w + p.cv_lw, h + p.cv_lh, n, tb, ta);
+            }
+        } else if (A_KC) {
             tma_load_3d(sa, &tmA, fb, k0, m0, batch);
         } else if (p.blocked & 1) {
             tma_load_4d(sa, &tmA, fb, 0, k0, m0 / 16, batch);          // the BM/16 blocks of [16 k][16 m] in ONE box
@@ -335,6 +382,134 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ----------------------------------------------------------------------------- filter gradient of a convolution
+// dW[(a,b,c), o] = sum_{n,oh,ow} x[n, oh+a, ow+b, c] * d[n, oh, ow, o]     (== Einsum('pk,po->ko', Im2Col(x), d))
+// As a GEMM over im2col blocks this is bound by the TMA unit, not the tensor pipe: every 128-byte image row (16 channels of one
+// pixel) feeds only 16 x 32 products, and each filter tap loads it again (measured 2.43 ms at configs[3], 8.5 TFLOP/s).  Here a
+// CTA owns one filter ROW a (and 16 channels x 32 outputs): one image row segment in shared memory serves all kw taps of that
+// filter row as kw overlapping views shifted by one 128-byte row each, so per stage the kernel loads SEG + kw - 1 image rows
+// and 2 x SEG gradient rows with three plain tiled TMA boxes and issues 2 kw x 2 x SEG/4 DMMAs per warp pair.
+//   warps 0-7: consumers; pair (w >> 1) takes every 4th stage (a 4-way split of the position sum whose partial results
+//              are separate slabs of the workspace, summed afterwards in a fixed order), w & 1 picks 16 of the 32 outputs
+//   warp 8   : TMA producer
+// Fragment addressing as in gemm_tma_kernel's MN-contiguous operands: one LDS.128 = two interleaved 8-wide tiles of one k-row.
+struct WgradParams {
+    int kw, C, O;
+    int cblocks, opairs;          // C / 16, ceil(O / 32)
+    int OH, nseg, SEG;            // output rows per image, segments per output row, positions per segment (multiple of 8)
+    int xrows;                    // image rows per stage: roundup(SEG + kw - 1, 8)
+    int chunks, chunks_per_split; // N * OH * nseg
+    double* ws;                   // [gridDim.y * 4][kh * kw * C][Np]
+    long long slab;               // kh * kw * C * Np
+    int Np;
+};
+constexpr int WG_STAGES = 8;
+
+template <int KW>
+__global__ void __launch_bounds__(288, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const WgradParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int x_bytes = p.xrows * 128, d_bytes = p.SEG * 128, stage_bytes = x_bytes + 2 * d_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * stage_bytes);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + WG_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // task = (filter row a, channel block cb, output pair op); blockIdx.y = split of the chunk range
+    int t = blockIdx.x;
+    const int op = t % p.opairs; t /= p.opairs;
+    const int cb = t % p.cblocks;
+    const int a = t / p.cblocks;
+    const int j0 = blockIdx.y * p.chunks_per_split;
+    const int j1 = min(j0 + p.chunks_per_split, p.chunks);
+    const int nch = max(j1 - j0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < nch; ++i) {
+                const int s = i % WG_STAGES;
+                mbar_wait(empty0 + 8 * s, ((i / WG_STAGES) & 1) ^ 1);
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, stage_bytes);
+                const int j = j0 + i;
+                const int seg = j % p.nseg;
+                const int row = j / p.nseg;               // n * OH + oh
+                const int n = row / p.OH, oh = row - n * p.OH;
+                const uint32_t sx = smem_u32(smem + s * stage_bytes);
+                tma_load_4d(sx, &tmX, fb, cb * 16, seg * p.SEG, oh + a, n);
+                tma_load_4d(sx + x_bytes, &tmD, fb, op * 32, seg * p.SEG, oh, n);
+                tma_load_4d(sx + x_bytes + d_bytes, &tmD, fb, op * 32 + 16, seg * p.SEG, oh, n);
+            }
+        }
+        return;
+    }
+    const int ob = warp & 1, wk = warp >> 1;
+    const int g = lane >> 2, q = lane & 3;
+    double acc[2 * KW][2][2];
+#pragma unroll
+    for (int i = 0; i < 2 * KW; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+    const int k8s = p.SEG >> 3;
+    int prev = -1;
+    for (int i = wk; i < nch; i += 4) {
+        const int s = i % WG_STAGES;
+        mbar_wait(full0 + 8 * s, (i / WG_STAGES) & 1);
+        // the previous stage of this warp goes back to the producer only now: every MMA that consumed it has issued, so every
+        // LDS that read it has completed (see the main loop of gemm_tma_kernel)
+        if (prev >= 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * prev);
+        }
+        prev = s;
+        const unsigned char* sx = smem + s * stage_bytes;
+        const unsigned char* sd = sx + x_bytes + ob * d_bytes;
+        for (int h = 0; h < k8s; ++h) {
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int kr = 8 * h + 2 * q + pp;
+                const double2 bv = lds128(sd + kr * 128 + ((g ^ (kr & 7)) << 4));
+                double av[2 * KW];
+#pragma unroll
+                for (int b = 0; b < KW; ++b) {
+                    const int xr = kr + b;
+                    const double2 v = lds128(sx + xr * 128 + ((g ^ (xr & 7)) << 4));
+                    av[2 * b] = v.x;
+                    av[2 * b + 1] = v.y;
+                }
+#pragma unroll
+                for (int m = 0; m < 2 * KW; ++m) {
+                    dmma884(acc[m][0][0], acc[m][0][1], av[m], bv.x);
+                    dmma884(acc[m][1][0], acc[m][1][1], av[m], bv.y);
+                }
+            }
+        }
+    }
+    // partial result of this warp: slab (split, wk), rows (a, b, cb*16 + 2g + e), columns op*32 + ob*16 + 4q + {0,1,2,3}
+    double* slab = p.ws + ((long long)blockIdx.y * 4 + wk) * p.slab;
+    const int col = op * 32 + ob * 16 + 4 * q;
+#pragma unroll
+    for (int m = 0; m < 2 * KW; ++m) {
+        const int b = m >> 1;
+        const long long row = ((long long)(a * p.kw + b)) * p.C + cb * 16 + 2 * g + (m & 1);
+        double* cp = slab + row * p.Np + col;
+        const double v0 = acc[m][0][0], v1 = acc[m][1][0], v2 = acc[m][0][1], v3 = acc[m][1][1];
+        if (col + 3 < p.Np) {
+            reinterpret_cast<double2*>(cp)[0] = make_double2(v0, v1);
+            reinterpret_cast<double2*>(cp)[1] = make_double2(v2, v3);
+        } else {
+            if (col < p.Np) cp[0] = v0;
+            if (col + 1 < p.Np) cp[1] = v1;
+            if (col + 2 < p.Np) cp[2] = v2;
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------- tail-wave fix-up
 // C tile = sum over the K-slices z (fixed order => deterministic) of the dense BM x BN partial tiles the tail launch wrote.
 __global__ void __launch_bounds__(256)
@@ -480,10 +655,10 @@ static bool tma_ok(const double* base, long long s_other, long long s_batch, lon
     return true;
 }
 
-template <class Cfg, bool A_KC, bool B_KC>
+template <class Cfg, bool A_KC, bool B_KC, int CONV = 0>
 static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, int splits, cudaStream_t st, int ntiles = -1) {
     static bool attr_set = false;
-    auto kern = gemm_tma_kernel<Cfg, A_KC, B_KC>;
+    auto kern = gemm_tma_kernel<Cfg, A_KC, B_KC, CONV>;
     constexpr int GEMM_SMEM = Cfg::SMEM;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -644,6 +819,7 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
             p.tile_offset = 0; p.ws_tiles = 0;
+            p.cv_wb = p.cv_hb = p.cv_lw = p.cv_lh = p.cv_kw = p.cv_cpt = 0;
             auto dispatch = [&](const GemmParams& pp, int sp, int ntiles) -> int {
                 if (skinny_s) {
                     if (a_kc && b_kc) return launch_tma<CfgSkinnyS, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
@@ -739,6 +915,233 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         count_launch();
     }
     return 0;
+}
+
+// ----------------------------------------------------------------------------- implicit-GEMM convolution
+// The im2col matrix of an NHWC image is never written: the GEMM's A tiles come straight from the image through an
+// im2col-mode tensor map.  At configs[3] the materialised matrix of the second
+// layer is 2.57 GB, written once and read twice per step, and its gradient another 2.57 GB written and read by col2im.
+static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+static bool load_encode_im2col() {
+    if (g_encode_im2col) return true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+    return true;
+}
+
+bool conv_image_ok(const adb_tensor* img, int kh, int kw, int pad_h, int pad_w) {
+    if (img->rank != 4) return false;
+    const long long N = img->shape[0], H = img->shape[1], W = img->shape[2], Cc = img->shape[3];
+    if (N < 1 || H < 1 || W < 1 || Cc < 16 || Cc % 16) return false;
+    if (img->stride[3] != 1) return false;
+    for (int k = 0; k < 3; ++k) if (img->stride[k] <= 0 || (img->stride[k] & 1)) return false;
+    if (reinterpret_cast<uintptr_t>(img->ptr) & 15) return false;
+    if (kh < 1 || kw < 1 || pad_h < 0 || pad_w < 0 || pad_h > 127 || pad_w > 127 || kh - 1 - pad_h > 128 || kw - 1 - pad_w > 128) return false;
+    const long long hb = H + 2 * pad_h - kh + 1, wb = W + 2 * pad_w - kw + 1;
+    if (hb < 1 || wb < 1 || N * hb * wb >= (1LL << 31) - 1024 || (long long)kh * kw * Cc >= (1LL << 31)) return false;
+    return load_encode() && load_encode_im2col();
+}
+
+static bool make_tmap_im2col(CUtensorMap* map, const adb_tensor* img, int kh, int kw, int pad_h, int pad_w, int pixels) {
+    cuuint64_t dims[4] = {(cuuint64_t)img->shape[3], (cuuint64_t)img->shape[2], (cuuint64_t)img->shape[1], (cuuint64_t)img->shape[0]};
+    cuuint64_t strides[3] = {(cuuint64_t)img->stride[2] * 8ull, (cuuint64_t)img->stride[1] * 8ull, (cuuint64_t)img->stride[0] * 8ull};
+    int lo[2] = {-pad_w, -pad_h}, up[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, img->ptr, dims, strides, lo, up, 16u, (cuuint32_t)pixels, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// The B operand (K x Nn, strides b_sk / b_sn) of a CONV launch: K-contiguous or N-contiguous, as in gemm_f64.
+static bool make_b_map(CUtensorMap* tb, const double* B, long long K, long long Nn, long long b_sk, long long b_sn, int bn, bool* b_kc, int* blocked) {
+    *b_kc = b_sk == 1;
+    if (!*b_kc && b_sn != 1) return false;
+    if (!tma_ok(B, *b_kc ? b_sn : b_sk, 2, 1)) return false;
+    if (*b_kc) return make_tmap(tb, B, K, Nn, 1, b_sn, 2, BK, bn);
+    if (blocked_ok(Nn, b_sk) && make_tmap_blocked(tb, B, Nn, K, 1, b_sk, 2, bn / 16)) { *blocked |= 2; return true; }
+    return make_tmap(tb, B, Nn, K, 1, b_sk, 2, 16, BK);
+}
+
+// out[(n,hp,wp), j] = sum_{a,b,c} img[n, hp - pad_h + a, wp - pad_w + b, c] * B[(a*kw + b)*C + c, j]
+//   pad = 0:      forward convolution            == Einsum('pk,ko->po', Im2Col(img), B)
+//   pad = k - 1:  data gradient (img = dOut, B = flipped filter)  == Col2Im(Einsum('po,ko->pk', dOut, W))
+int conv_gemm_cols(const adb_tensor* img, int kh, int kw, int pad_h, int pad_w, const double* B, long long b_sk, long long b_sn, long long Nn,
+                   double* out, long long c_sm, long long c_sn, cudaStream_t st) {
+    if (!conv_image_ok(img, kh, kw, pad_h, pad_w)) return set_error("conv_gemm: image not describable by an im2col tensor map");
+    const long long Cc = img->shape[3], hb = img->shape[1] + 2 * pad_h - kh + 1, wb = img->shape[2] + 2 * pad_w - kw + 1;
+    const long long M = img->shape[0] * hb * wb, K = (long long)kh * kw * Cc;
+    if (Nn < 1) return 0;
+    const int cfg = Nn <= 16 ? 0 : (Nn <= 32 ? 1 : 2);
+    const int bm = cfg == 2 ? CfgBig::BM : CfgSkinny::BM, bn = cfg == 0 ? CfgSkinny16::BN : (cfg == 1 ? CfgSkinny::BN : CfgBig::BN);
+    CUtensorMap ta, tb;
+    bool b_kc = false;
+    int blocked = 0;
+    if (!make_tmap_im2col(&ta, img, kh, kw, pad_h, pad_w, bm)) return set_error("conv_gemm: cuTensorMapEncodeIm2col rejected the image");
+    if (!make_b_map(&tb, B, K, Nn, b_sk, b_sn, bn, &b_kc, &blocked)) return set_error("conv_gemm: filter matrix not describable by a tensor map");
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.M = (int)M; p.N = (int)Nn; p.K = (int)K;
+    p.tiles_m = (int)((M + bm - 1) / bm); p.tiles_n = (int)((Nn + bn - 1) / bn);
+    p.kt_per_split = (int)(K / BK); p.blocked = blocked;
+    p.C = out; p.c_sm = c_sm; p.c_sn = c_sn;
+    p.cv_wb = (int)wb; p.cv_hb = (int)hb; p.cv_lw = -pad_w; p.cv_lh = -pad_h; p.cv_kw = kw; p.cv_cpt = (int)(Cc / 16);
+    if (cfg == 0) return b_kc ? launch_tma<CfgSkinny16, true, true, 1>(ta, tb, p, 1, 1, st) : launch_tma<CfgSkinny16, true, false, 1>(ta, tb, p, 1, 1, st);
+    if (cfg == 1) return b_kc ? launch_tma<CfgSkinny, true, true, 1>(ta, tb, p, 1, 1, st) : launch_tma<CfgSkinny, true, false, 1>(ta, tb, p, 1, 1, st);
+    return b_kc ? launch_tma<CfgBig, true, true, 1>(ta, tb, p, 1, 1, st) : launch_tma<CfgBig, true, false, 1>(ta, tb, p, 1, 1, st);
+}
+
+// 4-D tiled map of an NHWC array: dims (C, W, H, N), box (16 channels, rows pixels, 1, 1).
+static bool make_tmap_nhwc_rows(CUtensorMap* map, const double* base, long long Cn, long long Wn, long long Hn, long long Nn,
+                                long long s_w, long long s_h, long long s_n, int rows) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cn, (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Nn};
+    cuuint64_t strides[3] = {(cuuint64_t)s_w * 8ull, (cuuint64_t)s_h * 8ull, (cuuint64_t)s_n * 8ull};
+    cuuint32_t box[4] = {16u, (cuuint32_t)rows, 1u, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int KW>
+static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& td, const WgradParams& p, int tasks, int splits, int smem, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = conv_wgrad_kernel<KW>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_error("conv_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<dim3((unsigned)tasks, (unsigned)splits), 288, smem, st>>>(tx, td, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("conv_wgrad launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
+static int conv_wgrad_rows(const adb_tensor* img, int kh, int kw, const double* D, long long d_sp, long long O,
+                           double* out, long long c_sm, long long c_sn, cudaStream_t st) {
+    const long long Nn = img->shape[0], H = img->shape[1], W = img->shape[2], Cc = img->shape[3];
+    const long long OH = H - kh + 1, OW = W - kw + 1, M = (long long)kh * kw * Cc;
+    WgradParams p;
+    memset(&p, 0, sizeof p);
+    const long long owp = (OW + 7) / 8 * 8;
+    p.nseg = owp <= 64 ? 1 : (int)((OW + 63) / 64);
+    p.SEG = (int)(((OW + p.nseg - 1) / p.nseg + 7) / 8 * 8);
+    p.xrows = (p.SEG + kw - 1 + 7) / 8 * 8;
+    p.kw = kw; p.C = (int)Cc; p.O = (int)O; p.cblocks = (int)(Cc / 16); p.opairs = (int)((O + 31) / 32); p.OH = (int)OH;
+    const long long chunks = Nn * OH * p.nseg;
+    if (chunks >= (1LL << 31)) return set_error("conv_wgrad: too many positions");
+    p.chunks = (int)chunks;
+    const int tasks = kh * p.cblocks * p.opairs;
+    int splits = tasks >= 148 ? 1 : 148 / tasks;
+    if (splits > chunks / 8) splits = (int)(chunks / 8);
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = (int)((chunks + splits - 1) / splits);
+    splits = (int)((chunks + p.chunks_per_split - 1) / p.chunks_per_split);
+    p.Np = (int)((O + 3) & ~3LL);
+    p.slab = M * p.Np;
+    const int stage_bytes = (p.xrows + 2 * p.SEG) * 128;
+    const int smem = WG_STAGES * stage_bytes + 1024 + 2 * WG_STAGES * 8;
+    if (smem > 227 * 1024) return set_error("conv_wgrad: stage does not fit shared memory");
+    CUtensorMap tx, td;
+    if (!make_tmap_nhwc_rows(&tx, img->ptr, Cc, W, H, Nn, img->stride[2], img->stride[1], img->stride[0], p.xrows) ||
+        !make_tmap_nhwc_rows(&td, D, O, OW, OH, Nn, d_sp, OW * d_sp, OH * OW * d_sp, p.SEG))
+        return set_error("conv_wgrad: cuTensorMapEncodeTiled rejected the operands");
+    const int nslabs = splits * 4;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p.ws), (size_t)nslabs * p.slab * sizeof(double), st);
+    if (e != cudaSuccess) return set_error("conv_wgrad: workspace allocation failed: %s", cudaGetErrorString(e));
+    int rc;
+    switch (kw) {
+        case 1: rc = launch_wgrad<1>(tx, td, p, tasks, splits, smem, st); break;
+        case 2: rc = launch_wgrad<2>(tx, td, p, tasks, splits, smem, st); break;
+        case 3: rc = launch_wgrad<3>(tx, td, p, tasks, splits, smem, st); break;
+        case 4: rc = launch_wgrad<4>(tx, td, p, tasks, splits, smem, st); break;
+        case 5: rc = launch_wgrad<5>(tx, td, p, tasks, splits, smem, st); break;
+        case 6: rc = launch_wgrad<6>(tx, td, p, tasks, splits, smem, st); break;
+        default: rc = launch_wgrad<7>(tx, td, p, tasks, splits, smem, st); break;
+    }
+    if (rc == 0) {
+        ReduceSpec S;
+        memset(&S, 0, sizeof S);
+        S.n_ops = 1; S.n_o = 2; S.n_r = 1; S.group = 1;
+        S.odim[0] = O; S.odim[1] = M;
+        S.out_s[0] = c_sn; S.out_s[1] = c_sm;
+        S.op_os[0][0] = 1; S.op_os[0][1] = p.Np;
+        S.rdim[0] = nslabs; S.op_rs[0][0] = p.slab;
+        S.op[0] = p.ws; S.out = out;
+        rc = reduce_run(S, st);
+    }
+    cudaFreeAsync(p.ws, st);
+    return rc;
+}
+
+// out[(a*kw + b)*C + c, o] = sum_{(n,hp,wp)} img[n, hp + a, wp + b, c] * D[(n,hp,wp), o]     == Einsum('pk,po->ko', Im2Col(img), D)
+int conv_gemm_wgrad(const adb_tensor* img, int kh, int kw, const double* D, long long d_sp, long long d_so, long long O,
+                    double* out, long long c_sm, long long c_sn, cudaStream_t st) {
+    if (!conv_image_ok(img, kh, kw, 0, 0)) return set_error("conv_gemm: image not describable by an im2col tensor map");
+    const long long Cc = img->shape[3], hb = img->shape[1] - kh + 1, wb = img->shape[2] - kw + 1;
+    const long long P = img->shape[0] * hb * wb, M = (long long)kh * kw * Cc;
+    if (O < 1) return 0;
+    {
+        static int pref = -1;          // ADB_CONV_WGRAD=blocks: the im2col-block GEMM below instead of conv_wgrad_kernel (A/B measurements)
+        if (pref < 0) { const char* e = getenv("ADB_CONV_WGRAD"); pref = (e && !strcmp(e, "blocks")) ? 0 : 1; }
+        if (pref && kw <= 7 && d_so == 1 && d_sp >= O && (d_sp & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 && wb <= 4096)
+            return conv_wgrad_rows(img, kh, kw, D, d_sp, O, out, c_sm, c_sn, st);
+    }
+    const bool skinny = O <= 32;
+    const int bm = 128, bn = skinny ? CfgSkinnyS::BN : CfgBig::BN;
+    CUtensorMap ta, tb;
+    bool b_kc = false;
+    int blocked = 0;
+    if (!make_tmap_im2col(&ta, img, kh, kw, 0, 0, BK)) return set_error("conv_gemm: cuTensorMapEncodeIm2col rejected the image");
+    if (!make_b_map(&tb, D, P, O, d_sp, d_so, bn, &b_kc, &blocked)) return set_error("conv_gemm: output gradient not describable by a tensor map");
+    const long long tiles = ((M + bm - 1) / bm) * ((O + bn - 1) / bn), slots = skinny ? 296 : 148;
+    const int total_kt = (int)((P + BK - 1) / BK);
+    long long splits = slots / tiles;
+    if (splits > total_kt / 16) splits = total_kt / 16;
+    if (splits > 128) splits = 128;
+    if (splits < 1) splits = 1;
+    const int kt_per_split = (int)((total_kt + splits - 1) / splits);
+    splits = (total_kt + kt_per_split - 1) / kt_per_split;
+    const long long Np = (O + 1) & ~1LL;
+    double* ws = nullptr;
+    if (splits > 1) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)splits * M * Np * sizeof(double), st);
+        if (e != cudaSuccess) return set_error("conv_gemm: split-K workspace allocation failed: %s", cudaGetErrorString(e));
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.M = (int)M; p.N = (int)O; p.K = (int)P;
+    p.tiles_m = (int)((M + bm - 1) / bm); p.tiles_n = (int)((O + bn - 1) / bn);
+    p.kt_per_split = kt_per_split; p.blocked = blocked;
+    if (splits > 1) { p.C = ws; p.c_sm = Np; p.c_sn = 1; p.c_ss = M * Np; }
+    else { p.C = out; p.c_sm = c_sm; p.c_sn = c_sn; }
+    p.cv_wb = (int)wb; p.cv_hb = (int)hb; p.cv_kw = kw; p.cv_cpt = (int)(Cc / 16);
+    int rc;
+    if (skinny) rc = b_kc ? launch_tma<CfgSkinnyS, false, true, 1>(ta, tb, p, 1, (int)splits, st) : launch_tma<CfgSkinnyS, false, false, 1>(ta, tb, p, 1, (int)splits, st);
+    else rc = b_kc ? launch_tma<CfgBig, false, true, 1>(ta, tb, p, 1, (int)splits, st) : launch_tma<CfgBig, false, false, 1>(ta, tb, p, 1, (int)splits, st);
+    if (rc == 0 && splits > 1) {
+        ReduceSpec S;
+        memset(&S, 0, sizeof S);
+        S.n_ops = 1; S.n_o = 2; S.n_r = 1; S.group = 1;
+        S.odim[0] = O; S.odim[1] = M;
+        S.out_s[0] = c_sn; S.out_s[1] = c_sm;
+        S.op_os[0][0] = 1; S.op_os[0][1] = Np;
+        S.rdim[0] = splits; S.op_rs[0][0] = M * Np;
+        S.op[0] = ws; S.out = out;
+        rc = reduce_run(S, st);
+    }
+    if (ws) cudaFreeAsync(ws, st);
+    return rc;
 }
 
 }  // namespace adb

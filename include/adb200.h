@@ -161,6 +161,17 @@ ADB_API int adb_softmax_ce(const adb_tensor* labels, const adb_tensor* logits, c
 ADB_API int adb_im2col(const adb_tensor* x, int kh, int kw, const adb_tensor* cols, void* stream);
 ADB_API int adb_col2im(const adb_tensor* cols, int kh, int kw, const adb_tensor* dx, void* stream);
 
+/* ---- implicit-GEMM convolution: the contractions on either side of Im2Col / Col2Im WITHOUT the
+ *      materialised im2col matrix (im2col-mode TMA feeds the FP64 DMMA pipeline straight from the NHWC image).  Same values
+ *      as the adb_im2col / adb_einsum / adb_col2im sequence they replace (reference design: reshape.py:137-160 windows +
+ *      Einsum, high_level_ops.py:152-165).  kh x kw window, stride 1, VALID; C (mode 2: O) must be a multiple of 16.
+ *        mode 0  out (N*OH*OW, O)      = Im2Col(x) @ w            x: (N,H,W,C), w: (kh*kw*C, O)
+ *        mode 1  out (kh*kw*C, O)      = Im2Col(x)^T @ w          w := the output gradient (N*OH*OW, O)
+ *        mode 2  out (N,H,W,C) dense   = Col2Im(x' @ w^T)         x := the output gradient seen as (N,OH,OW,O)
+ *      adb_conv_gemm_ok returns 1 when these operands qualify (else the caller runs the three-call sequence). */
+ADB_API int adb_conv_gemm(int mode, const adb_tensor* x, int kh, int kw, const adb_tensor* w, const adb_tensor* out, void* stream);
+ADB_API int adb_conv_gemm_ok(int mode, const adb_tensor* x, int kh, int kw, const adb_tensor* w, const adb_tensor* out);
+
 /* ---- launch-tape replay as ONE CUDA graph (replaces the per-node Python recursion of reference
  *      node.py:42-46 for graphs that are evaluated again and again).  adb_graph_begin puts `capture_stream` (must not be
  *      the legacy default stream) into relaxed capture mode; every compute call issued on it afterwards is recorded

@@ -1071,3 +1071,51 @@ def test_einsum_pairwise_chain_beyond_the_oracle(ad):
     check(g[0](), ones @ (b @ c @ d @ f).T, what="d/da")
     check(g[2](), (a @ b).T @ ones @ (d @ f).T, what="d/dc")
     check(g[4](), (a @ b @ c @ d).T @ ones, what="d/df")
+
+
+def test_conv_implicit_gemm_matches_explicit_and_oracle(ad):
+    """Channel counts that are multiples of 16: the einsums around Im2Col / Col2Im read the image through im2col-mode TMA
+    (adb_conv_gemm; the plan makes the Im2Col and the gradient einsum under Col2Im virtual).  Values must equal the explicit
+    im2col -> einsum -> col2im path and the oracle, first and second order."""
+    from autodiff_b200 import _lib
+    from autodiff_b200.core import engine
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((3, 12, 11, 16)); w = rng.standard_normal((3, 3, 16, 32)) * 0.2; w2 = rng.standard_normal((2, 3, 32, 16)) * 0.2
+
+    def run(m):
+        X, W, W2 = m.Variable(x.copy(), name="x"), m.Variable(w.copy(), name="w"), m.Variable(w2.copy(), name="w2")
+        h = m.ReLU(m.Conv2D(X, W))
+        y = m.Tanh(m.Conv2D(h, W2))
+        g = m.grad(y, [X, W, W2])
+        gg = m.grad(g[1], [W])[0]
+        return [np.array(t()) for t in [y] + g + [gg]]
+    names, orig = [], _lib.call
+
+    def spy(name, *a):
+        names.append(name)
+        return orig(name, *a)
+    _lib.call = spy
+    try:
+        got = run(ad)
+        n_implicit, n_im2col = names.count("adb_conv_gemm"), names.count("adb_im2col")
+        engine.implicit_conv_enabled = False
+        del names[:]
+        explicit = run(ad)
+        assert names.count("adb_conv_gemm") == 0 and names.count("adb_im2col") > n_im2col
+    finally:
+        _lib.call = orig
+        engine.implicit_conv_enabled = True
+    assert n_implicit >= 6, (n_implicit, n_im2col)        # 2 forward + 2 filter gradients + 2 data gradients at least
+    ref = run(onp)
+    for a, b, c in zip(got, explicit, ref):
+        check(a, b, tol=1e-12, what="implicit vs explicit")
+        check(a, c, tol=1e-11, what="implicit vs oracle")
+    # through the evaluator with ALL outputs at once (shared Im2Col between the forward and the filter gradient), taped replays too
+    for rep in range(4):
+        X, W = ad.Variable(x, name="x"), ad.Variable(w, name="w")
+        y = ad.Einsum("nhwo->", ad.ReLU(ad.Conv2D(X, W)))
+        gs = ad.grad(y, [X, W])
+        ad.evaluate_many(gs + [y])
+        Xo, Wo = onp.Variable(x, name="x"), onp.Variable(w, name="w")
+        go = onp.grad(onp.Einsum("nhwo->", onp.ReLU(onp.Conv2D(Xo, Wo))), [Xo, Wo])
+        check(gs[0](), go[0](), tol=1e-11); check(gs[1](), go[1](), tol=1e-11)

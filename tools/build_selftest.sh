@@ -4,3 +4,4 @@
 set -e
 cd "$(dirname "$0")"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o gemm_selftest gemm_selftest.cu ../autodiff_b200/build/*.o
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o conv_selftest conv_selftest.cu ../autodiff_b200/build/*.o
