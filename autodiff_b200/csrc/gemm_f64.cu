@@ -142,7 +142,114 @@ struct GemmParams {
     int cv_wb, cv_hb;            // positions per row / rows per image of the bounding box the windows slide over
     int cv_lw, cv_lh;            // its lower corner (0 for a VALID convolution, -(k-1) for the data gradient's full convolution)
     int cv_kw, cv_cpt;           // taps per filter row; k-tiles (16 channels) per tap
+    // stream-K kernel (gemm_sk_kernel): tiles [0, dp_tiles) are taken whole, one per CTA; the k-tiles ("units") of the remaining
+    // tiles are dealt out evenly and contiguously to the last sk_ctas CTAs of the grid
+    int total_kt, batch;
+    long long tiles_total, dp_tiles, sk_units;
+    int sk_ctas;
+    double* sk_ws;               // [2 * sk_ctas] partial tiles, thread-major (see gemm_sk_kernel)
+    unsigned* sk_count;          // [tiles_total - dp_tiles] arrivals per split tile (zeroed by the host)
 };
+
+// One k-tile (BK = 16) of a warp tile: fragment loads (conflict-free under the 128B swizzle, see the header) + MT x NT x 4 DMMAs.
+template <class Cfg, bool A_KC, bool B_KC>
+__device__ __forceinline__ void ktile_mma(const unsigned char* sA, const unsigned char* sB, int g, int q, int rmap,
+                                          double (&acc)[Cfg::MT][Cfg::NT][2]) {
+    constexpr int MT = Cfg::MT, NT = Cfg::NT;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double a[2][MT], b[2][NT];
+        if (A_KC) {
+            const int ch = ((4 * h + q) ^ rmap) << 4;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const double2 v = lds128(sA + mt * 1024 + ch);
+                a[0][mt] = v.x;
+                a[1][mt] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int kr = 8 * h + 2 * q + pp;
+                const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
+#pragma unroll
+                for (int blk = 0; blk < MT / 2; ++blk) {
+                    const double2 v = lds128(sA + blk * 2048 + off);
+                    a[pp][2 * blk] = v.x;
+                    a[pp][2 * blk + 1] = v.y;
+                }
+            }
+        }
+        if (B_KC) {
+            const int ch = ((4 * h + q) ^ rmap) << 4;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double2 v = lds128(sB + nt * 1024 + ch);
+                b[0][nt] = v.x;
+                b[1][nt] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int kr = 8 * h + 2 * q + pp;
+                const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
+#pragma unroll
+                for (int blk = 0; blk < NT / 2; ++blk) {
+                    const double2 v = lds128(sB + blk * 2048 + off);
+                    b[pp][2 * blk] = v.x;
+                    b[pp][2 * blk + 1] = v.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
+    }
+}
+
+// Register epilogue: accumulators -> C (general strides; 16B vector stores when the n-stride is 1).
+template <class Cfg, bool A_KC, bool B_KC>
+__device__ __forceinline__ void store_acc(const double (&acc)[Cfg::MT][Cfg::NT][2], double* __restrict__ Cb, long long c_sm, long long c_sn,
+                                          int m0, int n0, int M, int N, int warp_m, int warp_n, int g, int q, int rmap) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, MT = Cfg::MT, NT = Cfg::NT, WM = Cfg::WM, WN = Cfg::WN;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int row = m0 + warp_m * (BM / WM) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
+        if (row >= M) continue;
+        double* crow = Cb + (long long)row * c_sm;
+        if (B_KC) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = n0 + warp_n * (BN / WN) + nt * 8 + q + 4 * e;
+                    if (col < N) crow[(long long)col * c_sn] = acc[mt][nt][e];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int blk = 0; blk < NT / 2; ++blk) {
+                // thread owns 4 consecutive columns: 4q + {0,1,2,3} = (e=0,j=0),(e=0,j=1),(e=1,j=0),(e=1,j=1)
+                const int col = n0 + warp_n * (BN / WN) + blk * 16 + 4 * q;
+                const double v0 = acc[mt][2 * blk][0], v1 = acc[mt][2 * blk + 1][0];
+                const double v2 = acc[mt][2 * blk][1], v3 = acc[mt][2 * blk + 1][1];
+                double* cp = crow + (long long)col * c_sn;
+                if (c_sn == 1 && col + 3 < N && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+                    reinterpret_cast<double2*>(cp)[0] = make_double2(v0, v1);
+                    reinterpret_cast<double2*>(cp)[1] = make_double2(v2, v3);
+                } else {
+                    if (col < N) cp[0] = v0;
+                    if (col + 1 < N) cp[c_sn] = v1;
+                    if (col + 2 < N) cp[2 * c_sn] = v2;
+                    if (col + 3 < N) cp[3 * c_sn] = v3;
+                }
+            }
+        }
+    }
+}
 
 // ----------------------------------------------------------------------------- TMA + DMMA kernel
 // CONV = 1: A is the im2col matrix of an NHWC image, read straight from the image by im2col-mode TMA:
@@ -285,60 +392,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) mbar_arrive(empty0 + 8 * ((kt - 1) % STAGES));
         }
         const unsigned char* st = smem + s * STAGE_BYTES;
-        const unsigned char* sA = st + a_off;
-        const unsigned char* sB = st + b_off;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            double a[2][MT], b[2][NT];
-            if (A_KC) {
-                const int ch = ((4 * h + q) ^ rmap) << 4;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const double2 v = lds128(sA + mt * 1024 + ch);
-                    a[0][mt] = v.x;
-                    a[1][mt] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int kr = 8 * h + 2 * q + pp;
-                    const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
-#pragma unroll
-                    for (int blk = 0; blk < MT / 2; ++blk) {
-                        const double2 v = lds128(sA + blk * 2048 + off);
-                        a[pp][2 * blk] = v.x;
-                        a[pp][2 * blk + 1] = v.y;
-                    }
-                }
-            }
-            if (B_KC) {
-                const int ch = ((4 * h + q) ^ rmap) << 4;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double2 v = lds128(sB + nt * 1024 + ch);
-                    b[0][nt] = v.x;
-                    b[1][nt] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int kr = 8 * h + 2 * q + pp;
-                    const int off = kr * 128 + ((g ^ (kr & 7)) << 4);
-#pragma unroll
-                    for (int blk = 0; blk < NT / 2; ++blk) {
-                        const double2 v = lds128(sB + blk * 2048 + off);
-                        b[pp][2 * blk] = v.x;
-                        b[pp][2 * blk + 1] = v.y;
-                    }
-                }
-            }
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[pp][mt], b[pp][nt]);
-        }
+        ktile_mma<Cfg, A_KC, B_KC>(st + a_off, st + b_off, g, q, rmap, acc);
     }
 
     // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
@@ -346,39 +400,241 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     double* __restrict__ Cb = p.ws_tiles > 0
         ? p.C + ((long long)blockIdx.z * p.ws_tiles + blockIdx.x) * (BM * BN) - ((long long)m0 * BN + n0)
         : p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        const int row = m0 + warp_m * (BM / WM) + (A_KC ? mt * 8 + rmap : (mt >> 1) * 16 + 2 * g + (mt & 1));
-        if (row >= p.M) continue;
-        double* crow = Cb + (long long)row * p.c_sm;
-        if (B_KC) {
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = n0 + warp_n * (BN / WN) + nt * 8 + q + 4 * e;
-                    if (col < p.N) crow[(long long)col * p.c_sn] = acc[mt][nt][e];
-                }
-            }
+    store_acc<Cfg, A_KC, B_KC>(acc, Cb, p.c_sm, p.c_sn, m0, n0, p.M, p.N, warp_m, warp_n, g, q, rmap);
+}
+
+// ----------------------------------------------------------------------------- stream-K kernel
+// ONE launch without wave quantisation.  Tiles in raster order; grid = dp_tiles + sk_ctas CTAs:
+//   * CTA x < dp_tiles computes tile x whole, with the loop of gemm_tma_kernel (dp_tiles is a multiple of the SM slots: these are
+//     the full waves, and the hardware's dynamic CTA scheduler keeps dealing them out as SMs free up);
+//   * the k-tiles ("units") of the remaining tiles - the wave that would fill only part of the machine - are dealt out evenly and
+//     contiguously to the last sk_ctas CTAs (<= one per SM slot, so they all run at once when the last full wave drains).  A CTA's
+//     share is a run of SEGMENTS (tile, [lo, hi)): at most one that starts inside a tile, whole tiles, at most one that ends inside
+//     a tile.  Its smem ring, mbarriers and producer run across segment boundaries, so the loads of the next segment are in flight
+//     while the accumulators of this one are stored.
+// A partial segment parks its accumulators thread-major in its own slot of the workspace (slot 2c for a segment of stream-K CTA c
+// that starts inside a tile, 2c + 1 for one that starts a tile), then bumps the tile's arrival counter; the CTA that arrives last
+// re-adds ALL parts of the tile in k order - the order, and therefore the rounding, does not depend on which CTA arrives last -
+// and stores the tile.  Nobody waits for anybody, so the kernel cannot deadlock whatever else shares the GPU.
+// (A fully persistent variant - whole tiles round-robin inside the same CTAs - measured 2 % slower per tile than relaunching CTAs:
+// profiles/r02_gemm_streamk.md.)
+struct SkCursor {         // (32-bit: the host keeps tiles_total and sk_units below 2^31)
+    int u, ue;            // units of the stream-K region still to take
+    int tile;             // current segment
+    int lo, hi;
+};
+__device__ __forceinline__ int sk_unit_begin(const GemmParams& p, int cta) {
+    return (int)((long long)cta * p.sk_units / p.sk_ctas);
+}
+__device__ __forceinline__ bool sk_advance(SkCursor& c, const GemmParams& p) {
+    if (c.u >= c.ue) return false;
+    const int t = c.u / p.total_kt;
+    c.lo = c.u - t * p.total_kt;
+    const int left = c.ue - c.u;
+    c.hi = (left < p.total_kt - c.lo) ? c.lo + left : p.total_kt;
+    c.tile = (int)p.dp_tiles + t;
+    c.u += c.hi - c.lo;
+    return true;
+}
+// stream-K CTA whose share holds unit u
+__device__ __forceinline__ int sk_owner(const GemmParams& p, int u) {
+    int c = (int)((long long)u * p.sk_ctas / p.sk_units);
+    if (c >= p.sk_ctas) c = p.sk_ctas - 1;
+    while (sk_unit_begin(p, c) > u) --c;
+    while (sk_unit_begin(p, c + 1) <= u) ++c;
+    return c;
+}
+template <int BM, int BN>
+__device__ __forceinline__ void sk_tile_origin(const GemmParams& p, int tile, int& m0, int& n0, int& batch) {
+    const int GROUP = 8;
+    const int tiles2d = p.tiles_m * p.tiles_n;
+    batch = tile / tiles2d;
+    const int t2 = tile - batch * tiles2d;
+    const int group_size = GROUP * p.tiles_n;
+    const int first_m = (t2 / group_size) * GROUP;
+    const int gm = min(p.tiles_m - first_m, GROUP);
+    m0 = (first_m + (t2 % group_size) % gm) * BM;
+    n0 = ((t2 % group_size) / gm) * BN;
+}
+
+template <class Cfg, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB)
+gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, STAGES = Cfg::STAGES, MT = Cfg::MT, NT = Cfg::NT;
+    constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, PREFETCH = Cfg::PREFETCH;
+    constexpr int ACC2 = MT * NT;                        // double2 values per thread
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = smem_u32(bars + STAGES);
+    volatile int* last_flag = reinterpret_cast<volatile int*>(bars + 2 * STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr int WM = Cfg::WM, WN = Cfg::WN;
+    const int warp_m = warp % WM;
+    const int warp_n = warp / WM;
+    const int g = lane >> 2;
+    const int q = lane & 3;
+    const int rmap = (g >> 1) | ((g & 1) << 2);
+    const int a_off = A_KC ? (warp_m * (BM / WM) + rmap) * 128 : warp_m * (MT / 2) * 2048;
+    const int b_off = A_TILE_BYTES + (B_KC ? (warp_n * (BN / WN) + rmap) * 128 : warp_n * (NT / 2) * 2048);
+    const bool is_producer = threadIdx.x == 0;
+
+    // one k-tile of tile (m0, n0, batch) into ring slot (it % STAGES)
+    auto issue = [&](int it, int kt, int m0, int n0, int batch) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t fb = full0 + 8 * s;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_TILE_BYTES;
+        const int k0 = kt * BK;
+        if (A_KC) {
+            tma_load_3d(sa, &tmA, fb, k0, m0, batch);
+        } else if (p.blocked & 1) {
+            tma_load_4d(sa, &tmA, fb, 0, k0, m0 / 16, batch);
         } else {
 #pragma unroll
-            for (int blk = 0; blk < NT / 2; ++blk) {
-                // thread owns 4 consecutive columns: 4q + {0,1,2,3} = (e=0,j=0),(e=0,j=1),(e=1,j=0),(e=1,j=1)
-                const int col = n0 + warp_n * (BN / WN) + blk * 16 + 4 * q;
-                const double v0 = acc[mt][2 * blk][0], v1 = acc[mt][2 * blk + 1][0];
-                const double v2 = acc[mt][2 * blk][1], v3 = acc[mt][2 * blk + 1][1];
-                double* cp = crow + (long long)col * p.c_sn;
-                if (p.c_sn == 1 && col + 3 < p.N && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-                    reinterpret_cast<double2*>(cp)[0] = make_double2(v0, v1);
-                    reinterpret_cast<double2*>(cp)[1] = make_double2(v2, v3);
-                } else {
-                    if (col < p.N) cp[0] = v0;
-                    if (col + 1 < p.N) cp[p.c_sn] = v1;
-                    if (col + 2 < p.N) cp[2 * p.c_sn] = v2;
-                    if (col + 3 < p.N) cp[3 * p.c_sn] = v3;
-                }
+            for (int b = 0; b < BM / 16; ++b) tma_load_3d(sa + b * 2048, &tmA, fb, m0 + 16 * b, k0, batch);
+        }
+        if (B_KC) {
+            tma_load_3d(sb, &tmB, fb, k0, n0, batch);
+        } else if (p.blocked & 2) {
+            tma_load_4d(sb, &tmB, fb, 0, k0, n0 / 16, batch);
+        } else {
+#pragma unroll
+            for (int b = 0; b < BN / 16; ++b) tma_load_3d(sb + b * 2048, &tmB, fb, n0 + 16 * b, k0, batch);
+        }
+    };
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if ((long long)blockIdx.x < p.dp_tiles) {
+        // ===== a whole tile: the loop of gemm_tma_kernel =====
+        int m0, n0, batch;
+        sk_tile_origin<BM, BN>(p, (int)blockIdx.x, m0, n0, batch);
+        const int num_kt = p.total_kt;
+        if (is_producer) {
+            const int npre = num_kt < PREFETCH ? num_kt : PREFETCH;
+            for (int kt = 0; kt < npre; ++kt) issue(kt, kt, m0, n0, batch);
+        }
+        for (int kt = 0; kt < num_kt; ++kt) {
+            if (is_producer && kt + PREFETCH < num_kt) issue(kt + PREFETCH, kt + PREFETCH, m0, n0, batch);
+            __syncwarp();
+            const int s = kt % STAGES;
+            mbar_wait(full0 + 8 * s, (kt / STAGES) & 1);
+            if (kt > 0) {                               // release of the PREVIOUS k-tile's slot: see gemm_tma_kernel
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * ((kt - 1) % STAGES));
+            }
+            const unsigned char* st = smem + s * STAGE_BYTES;
+            ktile_mma<Cfg, A_KC, B_KC>(st + a_off, st + b_off, g, q, rmap, acc);
+        }
+        store_acc<Cfg, A_KC, B_KC>(acc, p.C + (long long)batch * p.c_sb, p.c_sm, p.c_sn, m0, n0, p.M, p.N, warp_m, warp_n, g, q, rmap);
+        return;
+    }
+
+    // ===== a share of the stream-K region =====
+    const int cta = (int)(blockIdx.x - p.dp_tiles);
+    SkCursor pc, cc;                                    // producer (PREFETCH k-tiles ahead) and consumer cursors
+    cc.u = pc.u = sk_unit_begin(p, cta);
+    cc.ue = pc.ue = sk_unit_begin(p, cta + 1);
+    pc.tile = pc.lo = pc.hi = 0;
+    int p_kt = 0, p_m0 = 0, p_n0 = 0, p_batch = 0, p_it = 0;
+    bool p_more = true;
+    auto issue_next = [&]() {
+        if (p_kt >= pc.hi) {
+            if (!sk_advance(pc, p)) { p_more = false; return; }
+            p_kt = pc.lo;
+            sk_tile_origin<BM, BN>(p, pc.tile, p_m0, p_n0, p_batch);
+        }
+        issue(p_it, p_kt, p_m0, p_n0, p_batch);
+        ++p_kt;
+        ++p_it;
+    };
+    if (is_producer)
+        for (int k = 0; k < PREFETCH && p_more; ++k) issue_next();
+
+    int it = 0;
+    bool first = true;
+    while (sk_advance(cc, p)) {
+        if (!first) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+        first = false;
+        for (int kt = cc.lo; kt < cc.hi; ++kt, ++it) {
+            if (is_producer && p_more) issue_next();
+            __syncwarp();
+            const int s = it % STAGES;
+            mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+            if (it > 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * ((it - 1) % STAGES));
+            }
+            const unsigned char* st = smem + s * STAGE_BYTES;
+            ktile_mma<Cfg, A_KC, B_KC>(st + a_off, st + b_off, g, q, rmap, acc);
+        }
+
+        if (cc.lo > 0 || cc.hi < p.total_kt) {
+            // ---- partial segment: park the accumulators, count the arrival; the last arriver rebuilds the tile in k order
+            double2* slot = reinterpret_cast<double2*>(p.sk_ws) + ((long long)(2 * cta + (cc.lo > 0 ? 0 : 1)) * ACC2) * GEMM_THREADS + threadIdx.x;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) slot[(i * NT + j) * GEMM_THREADS] = make_double2(acc[i][j][0], acc[i][j][1]);
+            __threadfence();
+            __syncthreads();
+            const int t = cc.tile - (int)p.dp_tiles;
+            const int u0 = t * p.total_kt;
+            const int c_first = sk_owner(p, u0), c_last = sk_owner(p, u0 + p.total_kt - 1);
+            if (threadIdx.x == 0) {
+                const unsigned old = atomicAdd(p.sk_count + t, 1u);
+                *last_flag = (old == (unsigned)(c_last - c_first)) ? 1 : 0;
+            }
+            __syncthreads();
+            const bool last = *last_flag != 0;
+            __syncthreads();                            // (the flag is rewritten by the next partial segment)
+            if (!last) continue;
+            __threadfence();
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int c = c_first; c <= c_last; ++c) {
+                const double2* part = reinterpret_cast<const double2*>(p.sk_ws) + ((long long)(2 * c + (c == c_first ? 1 : 0)) * ACC2) * GEMM_THREADS + threadIdx.x;
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double2 v = __ldcg(part + (i * NT + j) * GEMM_THREADS);
+                        acc[i][j][0] += v.x;
+                        acc[i][j][1] += v.y;
+                    }
             }
         }
+        int m0, n0, batch;
+        sk_tile_origin<BM, BN>(p, cc.tile, m0, n0, batch);
+        store_acc<Cfg, A_KC, B_KC>(acc, p.C + (long long)batch * p.c_sb, p.c_sm, p.c_sn, m0, n0, p.M, p.N, warp_m, warp_n, g, q, rmap);
     }
 }
 
@@ -673,6 +929,66 @@ static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     return 0;
 }
 
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// Stream-K launch: fills in the schedule (see gemm_sk_kernel), allocates the partial-tile workspace when some tile
+// is split, launches ONE kernel.  min_units: a CTA's share of the stream-K region is never shorter than this many k-tiles.
+template <class Cfg, bool A_KC, bool B_KC>
+static int launch_sk(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int batch, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = gemm_sk_kernel<Cfg, A_KC, B_KC>;
+    constexpr int SMEM = Cfg::SMEM;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    static int min_units = -1;         // ADB_GEMM_SK_MIN_UNITS (experiments)
+    if (min_units < 0) { const char* e = getenv("ADB_GEMM_SK_MIN_UNITS"); min_units = e ? atoi(e) : 8; if (min_units < 1) min_units = 1; }
+    const long long slots = (long long)sm_count() * Cfg::MINB;
+    p.total_kt = (p.K + BK - 1) / BK;
+    p.batch = batch;
+    p.tiles_total = (long long)p.tiles_m * p.tiles_n * batch;
+    p.dp_tiles = p.tiles_total / slots * slots;            // the full waves
+    const long long rem = p.tiles_total - p.dp_tiles;
+    p.sk_units = rem * p.total_kt;
+    if (p.tiles_total >= (1LL << 31) - slots || p.sk_units >= (1LL << 31)) return set_error("gemm: problem too large for the stream-K schedule");
+    p.sk_ctas = 0;
+    p.sk_ws = nullptr; p.sk_count = nullptr;
+    if (rem > 0) {
+        long long c = p.sk_units / min_units;
+        if (c < rem) c = rem;
+        if (c > slots) c = slots;
+        p.sk_ctas = (int)c;
+    }
+    const long long grid = p.dp_tiles + p.sk_ctas;
+    void* ws = nullptr;
+    if (rem > 0 && p.sk_ctas != rem) {
+        const size_t tile_bytes = (size_t)Cfg::BM * Cfg::BN * sizeof(double);
+        const size_t ws_bytes = 2 * (size_t)p.sk_ctas * tile_bytes, cnt_bytes = ((size_t)rem * sizeof(unsigned) + 255) & ~(size_t)255;
+        cudaError_t e = cudaMallocAsync(&ws, ws_bytes + cnt_bytes, st);
+        if (e != cudaSuccess) return set_error("gemm: stream-K workspace allocation failed: %s", cudaGetErrorString(e));
+        p.sk_ws = reinterpret_cast<double*>(ws);
+        p.sk_count = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(ws) + ws_bytes);
+        e = cudaMemsetAsync(p.sk_count, 0, cnt_bytes, st);
+        if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm: stream-K counter reset failed: %s", cudaGetErrorString(e)); }
+    }
+    kern<<<(unsigned)grid, GEMM_THREADS, SMEM, st>>>(ta, tb, p);
+    cudaError_t e = cudaGetLastError();
+    if (ws) cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) return set_error("gemm_sk launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
+
 int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
     const long long M = d->M, N = d->N, K = d->K, batch = d->batch;
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
@@ -766,14 +1082,24 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         static int tail_pref = -1;     // ADB_GEMM_TAIL=0: off (A/B measurements)
         if (tail_pref < 0) { const char* e = getenv("ADB_GEMM_TAIL"); tail_pref = (e && e[0] == '0') ? 0 : 1; }
         const bool big_tail = tail_pref && batch == 1 && big_tiles >= 296 && big_tiles % 148 > 0 && (big_tiles % 148) * 2 <= 148 && K >= 3072;
-        const bool small = !skinny && !skinny_s && (force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && ((waste_big > 1.05 && !big_tail) || short_k)))));
+        // Persistent stream-K kernel (one launch, no wave quantisation): forced by path 7 (128x128 tiles) / 8 (64x64 tiles);
+        // chosen automatically for 128x128-tile problems whose k-loop is long enough to hide a tile's epilogue.
+        static int sk_pref = -1;       // ADB_GEMM_SK=0: the one-tile-per-CTA kernels (A/B measurements)
+        if (sk_pref < 0) { const char* e = getenv("ADB_GEMM_SK"); sk_pref = (e && e[0] == '0') ? 0 : 1; }
+        const double fill_big = (double)M * (double)N / ((double)((M + 127) / 128 * 128) * (double)((N + 127) / 128 * 128));
+        // (measured, profiles/r02_gemm_streamk.md: with at least one full wave it never loses; below one wave every tile is split and
+        // the parked partial tiles cost more than the 64x64-tile kernel's idle SMs unless a CTA's share is a few dozen k-tiles)
+        const bool sk_auto = sk_pref && force_path == 0 && tile_pref == 0 && !skinny && !skinny_s && !short_k && batch <= 65535 &&
+                             fill_big >= 0.75 && (big_tiles >= 148 || big_tiles * ((K + BK - 1) / BK) >= 148 * 48);
+        const bool sk_big = force_path == 7 || sk_auto, sk_small = force_path == 8;
+        const bool small = !sk_big && !skinny && !skinny_s && (sk_small || force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && ((waste_big > 1.05 && !big_tail) || short_k)))));
         const int bm = skinny_s ? CfgSkinnyS::BM : skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM;
         const int bn = skinny_s ? CfgSkinnyS::BN : skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
         const long long slots = (small || skinny_s) ? 296 : 148;
         const int total_kt = (int)((K + BK - 1) / BK);
         int splits = 1;
-        if (tiles * 2 <= slots && total_kt >= 32) {
+        if (!sk_big && !sk_small && tiles * 2 <= slots && total_kt >= 32) {
             long long s1 = slots / tiles;
             if (s1 > total_kt / 16) s1 = total_kt / 16;
             if (s1 > 128) s1 = 128;
@@ -812,6 +1138,7 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         }
         if (ok) {
             GemmParams p;
+            memset(&p, 0, sizeof p);
             p.M = (int)M; p.N = (int)N; p.K = (int)K;
             p.tiles_m = (int)((M + bm - 1) / bm);
             p.tiles_n = (int)((N + bn - 1) / bn);
@@ -820,6 +1147,21 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
             p.tile_offset = 0; p.ws_tiles = 0;
             p.cv_wb = p.cv_hb = p.cv_lw = p.cv_lh = p.cv_kw = p.cv_cpt = 0;
+            if (sk_big || sk_small) {
+                int rc;
+                if (sk_big) {
+                    if (a_kc && b_kc) rc = launch_sk<CfgBig, true, true>(ta, tb, p, (int)batch, st);
+                    else if (a_kc && !b_kc) rc = launch_sk<CfgBig, true, false>(ta, tb, p, (int)batch, st);
+                    else if (!a_kc && b_kc) rc = launch_sk<CfgBig, false, true>(ta, tb, p, (int)batch, st);
+                    else rc = launch_sk<CfgBig, false, false>(ta, tb, p, (int)batch, st);
+                } else {
+                    if (a_kc && b_kc) rc = launch_sk<CfgSmall, true, true>(ta, tb, p, (int)batch, st);
+                    else if (a_kc && !b_kc) rc = launch_sk<CfgSmall, true, false>(ta, tb, p, (int)batch, st);
+                    else if (!a_kc && b_kc) rc = launch_sk<CfgSmall, false, true>(ta, tb, p, (int)batch, st);
+                    else rc = launch_sk<CfgSmall, false, false>(ta, tb, p, (int)batch, st);
+                }
+                return rc;
+            }
             auto dispatch = [&](const GemmParams& pp, int sp, int ntiles) -> int {
                 if (skinny_s) {
                     if (a_kc && b_kc) return launch_tma<CfgSkinnyS, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);

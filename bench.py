@@ -197,7 +197,7 @@ def run_gpu(args):
         avg = sum(gemm_ms) / len(gemm_ms)
         achieved = gemm_flops / (avg * 1e-3) / 1e12
         peak = float(peaks.get("dmma_issue_peak_tflops", 37.03))
-        roof = {"bound": "tensor", "kernel": "gemm_tma_kernel (FP64 DMMA.8x8x4), C2a launches 2*8192^3 flop each",
+        roof = {"bound": "tensor", "kernel": "gemm_sk_kernel (stream-K, FP64 DMMA.8x8x4), C2a launches 2*8192^3 flop each",
                 "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "avg_launch_ms": round(avg, 4), "launches_timed": len(gemm_ms), "traffic": peaks.get("c2a_gemm_dram_bytes_per_launch"),
                 "peak_source": "measured DMMA.8x8x4 issue-rate peak on this pool's B200 (profiles/r01_probe_fp64_issue_rates.log); "

@@ -291,6 +291,40 @@ def test_gemm_c_abi_all_layouts(ad):
                     check(Ct.cpu().numpy(), A @ B, what="gemm %s path %d" % ((M, N, K, nb, a_kc, b_kc), path))
 
 
+def test_gemm_stream_k(ad):
+    """The stream-K kernel (csrc/gemm_f64.cu: gemm_sk_kernel; forced paths 7 = 128x128 tiles, 8 = 64x64 tiles, and the automatic
+    choice): whole-tile CTAs plus CTAs that share the tiles of the ragged last wave along K.  Values against numpy's matmul, and
+    bitwise run-to-run repeatability - the parts of a split tile are re-added in k order whichever CTA arrives last."""
+    import torch
+    from autodiff_b200 import _lib
+    rng = np.random.default_rng(7)
+    cases = [(384, 256, 1024, 1), (1000, 520, 333, 2), (2176, 2176, 528, 1), (1281, 2047, 1000, 1), (640, 640, 4098, 1), (256, 256, 272, 37)]
+    for (M, N, K, nb) in cases:
+        for a_kc, b_kc in ((True, False), (False, True), (True, True), (False, False)):
+            A = rng.standard_normal((nb, M, K)); B = rng.standard_normal((nb, K, N))
+            Ah = A if a_kc else np.ascontiguousarray(A.transpose(0, 2, 1))
+            Bh = np.ascontiguousarray(B.transpose(0, 2, 1)) if b_kc else B
+            At, Bt = torch.from_numpy(Ah).cuda(), torch.from_numpy(Bh).cuda()
+            Ct = torch.empty((nb, M, N), dtype=torch.float64, device="cuda")
+            d = _lib.GemmDesc()
+            d.M, d.N, d.K, d.batch = M, N, K, nb
+            d.A, d.B, d.C = At.data_ptr(), Bt.data_ptr(), Ct.data_ptr()
+            d.a_sm, d.a_sk, d.a_sb = (K, 1, M * K) if a_kc else (1, M, M * K)
+            d.b_sk, d.b_sn, d.b_sb = (1, K, N * K) if b_kc else (N, 1, N * K)
+            d.c_sm, d.c_sn, d.c_sb = N, 1, M * N
+            aligned = (K % 2 == 0 if a_kc else M % 2 == 0) and (K % 2 == 0 if b_kc else N % 2 == 0)
+            want = A @ B
+            for path in ((7, 8, 0) if aligned else (0,)):
+                runs = []
+                for _ in range(3):
+                    Ct.fill_(float("nan"))
+                    _lib.check(_lib.lib().adb_gemm_f64_path(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream), path))
+                    torch.cuda.synchronize()
+                    runs.append(Ct.cpu().numpy())
+                check(runs[0], want, what="stream-K gemm %s path %d" % ((M, N, K, nb, a_kc, b_kc), path))
+                assert all(np.array_equal(runs[0], r) for r in runs[1:]), "stream-K result differs from run to run: %s path %d" % ((M, N, K, nb), path)
+
+
 @pytest.mark.parametrize("spec,shapes", [
     ("ik,jk->ij", [(1152, 1024), (1027, 1024)]), ("ij,jk->ik", [(1152, 1024), (1024, 1028)]), ("ij,jk->ki", [(2050, 768), (768, 1152)]),
     ("ik,jk->ij", [(1152, 1024), (2049, 1024)]), ("ij,jk->ik", [(1152, 640), (640, 2050)]),

@@ -180,6 +180,10 @@ static int run_tf32(long long M, long long N, long long K, long long nb, int a_k
 int main(int argc, char** argv) {
     bool quick = argc > 1 && !strcmp(argv[1], "quick");
     if (adb_init(0)) { printf("adb_init failed: %s\n", adb_last_error()); return 1; }
+    if (argc > 8 && !strcmp(argv[1], "one")) {             // one timed case: one M N K batch a_kc b_kc path   (for ncu)
+        run_case(Case{atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoll(argv[5]), atoi(argv[6]), atoi(argv[7]), 0, atoi(argv[8])}, true, 2);
+        return 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "tf32")) {
         int fails = 0;
         long long shapes[][4] = {{128, 128, 32, 1}, {128, 128, 256, 1}, {256, 384, 100, 1}, {200, 136, 77, 1}, {257, 129, 50, 3}, {1000, 520, 333, 2}, {64, 64, 1024, 1}};
@@ -234,6 +238,34 @@ int main(int argc, char** argv) {
             }
         }
         return fails ? 1 : 0;
+    }
+    if (argc > 1 && !strcmp(argv[1], "sk")) {              // persistent stream-K kernel: paths 7 (128x128 tiles) and 8 (64x64 tiles)
+        int f = 0;
+        for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) {
+            long long shapes[][4] = {{128, 128, 16, 1}, {128, 128, 96, 1}, {64, 40, 24, 1}, {200, 136, 100, 1}, {257, 129, 50, 3}, {1000, 520, 333, 2},
+                                     {130, 130, 1, 1}, {384, 256, 1024, 1}, {512, 1024, 1024, 1}, {1280, 2048, 1024, 1}, {1281, 2047, 1000, 1},
+                                     {1000, 3970, 777, 1}, {640, 640, 4097, 1}, {300, 200, 8000, 1}, {256, 256, 272, 37}, {2176, 2176, 528, 1}};
+            for (auto& s : shapes) for (int path : {7, 8}) f += run_case(Case{s[0], s[1], s[2], s[3], a, b, 0, path}, false, 0);
+        }
+        printf("stream-K correctness: %d failing cases\n", f);
+        // run-to-run bitwise repeatability is checked by tests/test_gpu_parity.py; here: speed against the one-tile-per-CTA kernels
+        long long shp[][5] = {{1024, 4096, 4097, 1, 1}, {1024, 4096, 4096, 1, 3}, {4096, 4096, 1024, 1, 0}, {2048, 4096, 4097, 1, 1}, {4097, 4096, 2048, 1, 0},
+                              {512, 1024, 1024, 1, 1}, {512, 1024, 1024, 1, 3}, {1024, 1024, 512, 1, 0}, {512, 71, 1024, 1, 1}, {71, 1024, 512, 1, 0},
+                              {8192, 4096, 4097, 1, 1}, {4097, 4096, 8192, 1, 0}, {8192, 8192, 8192, 1, 1}, {8192, 8192, 8192, 1, 3}, {8192, 8192, 8192, 1, 0},
+                              {1024, 1024, 1024, 64, 1}, {2048, 2048, 2048, 1, 1}, {4096, 4096, 4096, 1, 1}};
+        for (auto& s : shp) {
+            const int a_kc = (s[4] & 1) ? 1 : 0, b_kc = (s[4] & 2) ? 1 : 0;
+            for (int path : {0, 3, 4, 7, 8}) {
+                if ((path == 3 || path == 8) && s[0] * s[1] * s[3] >= 8192ll * 4096) continue;
+                run_case(Case{s[0], s[1], s[2], s[3], a_kc, b_kc, 0, path}, true, 5);
+            }
+        }
+        return f ? 1 : 0;
+    }
+    if (argc > 1 && !strcmp(argv[1], "skab")) {            // stream-K against one tile per CTA on whole-wave and ragged-wave shapes
+        long long shp[][5] = {{4736, 4096, 4096, 1, 1}, {1024, 1024, 4096, 1, 1}, {512, 1024, 4096, 1, 1}, {1024, 1024, 2048, 1, 1}, {1024, 1024, 1024, 1, 1}, {1024, 2048, 1024, 1, 1}, {512, 1024, 2048, 1, 1}, {768, 768, 768, 1, 1}, {512, 1024, 1024, 1, 1}};
+        for (auto& s : shp) for (int path : {3, 4, 7}) run_case(Case{s[0], s[1], s[2], s[3], (int)(s[4] & 1), (int)((s[4] >> 1) & 1), 0, path}, true, 5);
+        return 0;
     }
     if (argc > 1 && !strcmp(argv[1], "tail")) {            // shapes whose last wave is split along K (ADB_GEMM_TAIL=0 turns it off)
         run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 0}, true, 5);    // C3 forward on a 1024-row shard
