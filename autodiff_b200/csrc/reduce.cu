@@ -894,6 +894,70 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
     }
 }
 
+// Narrow rows (cols <= 512): one WARP per row, the row of logits and labels in registers (K quads per lane each), every
+// reduction a shuffle - no shared memory, no block barrier, and a CTA's 8 warps work on 8 rows whose loads are all in flight
+// together.  (The one-CTA-per-row kernel above at 512 columns: half its threads hold padding and every row pays a
+// __syncthreads - 0.39 of the HBM roof, profiles/r01_kernel_microbench_v9.log; C5's per-step loss and C1/C3's 10-class
+// losses are this shape class.)  Same arithmetic as the wide kernel with NW = 1.
+template <int K>
+__global__ void __launch_bounds__(256) softmax_ce_warp_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
+                                                              long long z_sr, double* __restrict__ out, long long o_s, long long rows,
+                                                              unsigned cols, int* __restrict__ flag) {
+    const unsigned lane = threadIdx.x & 31;
+    const long long wstep = (long long)gridDim.x * 8;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstep) {
+        const double* z = logits + r * z_sr;
+        const double* l = labels + r * l_sr;
+        Quad zq[K], lq[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const unsigned c = (k * 32u + lane) * 4u;
+            if (c + 3 < cols) {
+                zq[k] = ldq(z + c);
+                lq[k] = ldq(l + c);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    zq[k].v[e] = c + e < cols ? __ldg(z + c + e) : -INFINITY;   // neutral: never the max, exp() = 0, label 0
+                    lq[k].v[e] = c + e < cols ? __ldg(l + c + e) : 0.0;
+                }
+            }
+        }
+        double m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m = fmax(m, zq[k].v[e]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        const double mm = m == -INFINITY ? 0.0 : m;      // (fmax skips NaN, exp_nonpos does not: a NaN logit makes `se` NaN)
+        double se = 0.0, lsum = 0.0, dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned c = (k * 32u + lane) * 4u + e;
+                se += exp_nonpos(zq[k].v[e] - mm);
+                dot += c < cols ? lq[k].v[e] * zq[k].v[e] : 0.0;
+                lsum += lq[k].v[e];
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, off);
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+            dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        }
+        if (lane == 0) {
+            if (m == -INFINITY) se = NAN;              // a row of -inf: numpy computes exp(-inf - -inf) = nan
+            const double lse = m + log(se);
+            out[r * o_s] = -(dot - lse * lsum);
+            if (!(fabs(lsum - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+        }
+    }
+}
+
 // (A TMA-staged persistent variant - one 512-thread CTA per SM, rows prefetched into a shared-memory ring with 1-D bulk
 // copies - was measured at 0.47 of the HBM roof against 0.66 for the kernel above: with 64 KB per row only one CTA fits
 // per SM, and the per-row dependent chain (max -> exp -> sum -> log) then has no second CTA to overlap with.)
@@ -915,7 +979,21 @@ int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb
         const int r = softmax_ce_ring_try(labels, logits, out, flag, st);     // persistent ring kernel (softmax_ce_ring.cu)
         if (r >= 0) return r;
     }
-    if (quad_ok && cols >= 512 && cols <= 8192 && rows < (1LL << 31)) {
+    static int warp_rows = -1;                    // ADB_SCE_WARP=0: the round-1 dispatch (A/B measurements)
+    if (warp_rows < 0) { const char* e = getenv("ADB_SCE_WARP"); warp_rows = (e && e[0] == '0') ? 0 : 1; }
+    // (measured, profiles/r02_softmax_ce_warp.log: 0.16 -> 0.32 of the HBM roof at 64 columns, 0.36 -> 0.61 at 128, 0.46 -> 0.74 at 256,
+    // 0.39 -> 0.71 at 512; beyond 512 columns a lane would hold 8 + 8 quads - 183 registers, one CTA per SM - and the
+    // one-CTA-per-row kernel below wins: 0.56 at 768, 0.71 at 1024)
+    if (quad_ok && warp_rows && cols <= 512) {
+        long long blocks = (rows + 7) / 8;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+#define ADB_SCEW(KK) softmax_ce_warp_kernel<KK><<<(unsigned)blocks, 256, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
+                                                                                   out->stride[0], rows, (unsigned)cols, flag)
+        if (cols <= 128) ADB_SCEW(1);
+        else if (cols <= 256) ADB_SCEW(2);
+        else ADB_SCEW(4);
+#undef ADB_SCEW
+    } else if (quad_ok && cols >= 512 && cols <= 8192 && rows < (1LL << 31)) {
         const unsigned g = (unsigned)rows;
 #define ADB_SCE(KK, NTT) softmax_ce_wide_kernel<KK, NTT><<<g, NTT, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
                                                                             out->stride[0], rows, (unsigned)cols, flag)

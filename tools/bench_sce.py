@@ -36,6 +36,14 @@ for cols in widths:
     l[np.arange(rows), rng.integers(0, cols, rows)] = 1.0
     ld = ad.to_device(l)
     z = zf.getitem(slice(0, rows * cols)).reshape_view((rows, cols))
+    if os.environ.get("BENCH_SCE_SIMPLE"):        # the default dispatch only (run once per ADB_SCE_WARP setting: read once per process)
+        for _ in range(3):
+            run(z, ld, 2)
+        ms = min(run(z, ld) for _ in range(5))
+        nbytes = 8 * (2 * rows * cols + rows)
+        print({"rows": rows, "cols": cols, "ms": round(ms, 4), "frac": round(nbytes / ms / 1e6 / PEAK, 3), "warp_kernel": os.environ.get("ADB_SCE_WARP", "1")}, flush=True)
+        del ld
+        continue
     out = {}
     for ring in ("1", "0"):
         os.environ["ADB_SCE_RING"] = ring
