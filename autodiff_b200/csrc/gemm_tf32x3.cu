@@ -7,13 +7,17 @@
 //   A.B ~= hi_A.hi_B + lo_A.hi_B + hi_A.lo_B          (three tcgen05.mma per k-step, fp32 accumulation in TMEM)
 // which gives ~1e-7 relative error.
 //
-//   split_tf32_kernel : fp64 (any strides) -> two K-major fp32 matrices (hi, lo) per operand, zero-padded pitch
+//   split_tf32_kernel / split_tf32_t_kernel : fp64 (any strides) -> two K-major fp32 matrices (hi, lo) per operand, zero-padded
+//                       pitch; the _t variant transposes 32 x 32 tiles through shared memory for MN-contiguous operands
 //   gemm_tf32x3_kernel<MT>: TMA (128B swizzle) -> smem ring -> tcgen05.mma.kind::tf32 (M=128, N=128, K=8) issued by one
-//                       thread, MT accumulators of 128 TMEM columns each -> tcgen05.ld -> fp64 -> C.  MT = 2 stacks two
-//                       128-row tiles on the same B tiles (256x128 per CTA, 2 stages of 96 KiB); measured 8192^3:
-//                       6.15 ms vs 6.40 ms for MT = 1 (3 stages of 64 KiB), i.e. ~215 TFLOP/s effective = 645 TFLOP/s of
-//                       raw tf32 MMA inside the GEMM kernel, ~0.78 of what the cuBLAS bf16 burst figure of this pool
-//                       (1683 of 2250 nominal) suggests a tf32 kernel can sustain
+//                       thread, MT accumulators of 128 TMEM columns each, TWO such sets -> tcgen05.ld -> fp64 -> C.  MT = 2
+//                       stacks two 128-row tiles on the same B tiles (256x128 per CTA, 2 stages of 96 KiB).  K runs in
+//                       chains of <= 2048 (fp32 accumulation error grows with the chain): chain c + 1 fills one TMEM set
+//                       while the four epilogue warps add chain c to C in fp64.
+//                       Measured at 8192^3 (profiles/r02_ncu_summary.md): kernel 4.86 ms = 678 TFLOP/s of raw tf32 MMA = 0.90 of
+//                       the cuBLAS TF32 burst rate of this pool (753; profiles/tf32_peak.json), 5.30 ms with the split passes
+//                       = 207 TFLOP/s effective (round 1, chains as separate CTAs + a reduction kernel, column-major tile
+//                       order: 6.2 ms, 11.5 GB of DRAM reads per launch against 5.9 GB now)
 //   warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (one TMEM lane quadrant each)
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,8 +41,9 @@ template <int MT>
 struct Cfg {
     static constexpr int STAGES = MT == 1 ? 3 : 2;
     static constexpr int STAGE_BYTES = (2 * MT + 2) * TILE_BYTES;     // A_hi, A_lo (MT tiles each), B_hi, B_lo
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 64;
-    static constexpr int TMEM_COLS = 128 * MT;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 128;
+    static constexpr int ACC_COLS = 128 * MT;        // one accumulator set (MT tiles of 128 columns)
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;   // two sets: the epilogue drains chunk c while the MMAs fill chunk c + 1
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,41 +110,50 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 struct Params {
     int M, N, K;
     int tiles_m, tiles_n;
-    int kb_per_split, _pad;          // k-blocks per blockIdx.z (K is chunked so fp32 accumulation chains stay short)
+    int kb_per_chunk, _pad;          // k-blocks per accumulation chain (K is chunked so fp32 chains stay short, see gemm_tf32x3)
     double* C;
-    long long c_sm, c_sn, c_sb, c_ss;
+    long long c_sm, c_sn, c_sb;
 };
 
 template <int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const Params p) {
-    constexpr int STAGES = Cfg<MT>::STAGES, STAGE_BYTES = Cfg<MT>::STAGE_BYTES, TMEM_COLS = Cfg<MT>::TMEM_COLS;
+    constexpr int STAGES = Cfg<MT>::STAGES, STAGE_BYTES = Cfg<MT>::STAGE_BYTES, TMEM_COLS = Cfg<MT>::TMEM_COLS, ACC_COLS = Cfg<MT>::ACC_COLS;
     constexpr int A_BYTES = MT * TILE_BYTES;          // one A matrix (hi or lo) of a stage
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = smem_u32(bars + STAGES);
-    const uint32_t tmem_full = smem_u32(bars + 2 * STAGES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const uint32_t tmem_full0 = smem_u32(bars + 2 * STAGES);          // [2]: accumulator set complete (MMA -> epilogue)
+    const uint32_t tmem_empty0 = smem_u32(bars + 2 * STAGES + 2);     // [2]: accumulator set drained (epilogue -> MMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // grouped rasterisation (as gemm_f64.cu): the CTAs of a wave cover 8 tile-rows x ~18 tile-columns, so a wave reads 8 A panels
+    // and ~18 B panels instead of every A panel (ncu, 8192^3 with the column-major order: 11.5 GB of DRAM reads for 1 GB of operands)
+    const int GROUP = 8;
     const int tile = blockIdx.x;
-    const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+    const int group_size = GROUP * p.tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(p.tiles_m - first_m, GROUP);
+    const int tm = first_m + (tile % group_size) % gm, tn = (tile % group_size) / gm;
     const int m0 = tm * BM * MT, n0 = tn * BN;
     const int batch = blockIdx.y;
     const int total_kb = (p.K + BK - 1) / BK;
-    const int kb_first = blockIdx.z * p.kb_per_split;
-    const int num_kb = min(p.kb_per_split, total_kb - kb_first);
+    const int chunks = (total_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full0 + 8 * s, 1);
+            mbar_init(tmem_empty0 + 8 * s, 4);        // lane 0 of each of the four epilogue warps
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -153,16 +167,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: all k-blocks of the tile, chunk after chunk =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = 0; kb < total_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, STAGE_BYTES);
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const int k0 = (kb_first + kb) * BK;
+                const int k0 = kb * BK;
                 tma_load_3d(st, &tmAh, fb, k0, m0, batch);                       // box = (BK, 128 * MT rows)
                 tma_load_3d(st + A_BYTES, &tmAl, fb, k0, m0, batch);
                 tma_load_3d(st + 2 * A_BYTES, &tmBh, fb, k0, n0, batch);
@@ -170,74 +184,143 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread drives the tensor core for the whole CTA =====
+        // ===== MMA issuer: one thread drives the tensor core for the whole CTA.  Chunk c accumulates into TMEM set c & 1. =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc();
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full0 + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t dBh = make_desc(st + 2 * A_BYTES), dBl = make_desc(st + 2 * A_BYTES + TILE_BYTES);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {           // accumulator mt = TMEM columns [128 * mt, +128), A rows [128 * mt, +128)
-                    const uint64_t dAh = make_desc(st + mt * TILE_BYTES), dAl = make_desc(st + A_BYTES + mt * TILE_BYTES);
-                    const uint32_t acc = tmem_base + (uint32_t)(mt * BN);
-#pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K = 8 step inside the swizzled row
-                        umma_tf32(acc, dAl + adv, dBh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
-                        umma_tf32(acc, dAh + adv, dBl + adv, idesc, 1u);
-                        umma_tf32(acc, dAh + adv, dBh + adv, idesc, 1u);
-                    }
+            int kb = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int set = c & 1;
+                if (c >= 2) {                                            // the epilogue has drained chunk c - 2 out of this set
+                    mbar_wait(tmem_empty0 + 8 * set, ((c >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                umma_commit(empty0 + 8 * s);           // frees the smem slot once these MMAs have read it
+                const int kb_end = min(kb + p.kb_per_chunk, total_kb);
+                for (bool first = true; kb < kb_end; ++kb, first = false) {
+                    const int s = kb % STAGES;
+                    const uint32_t ph = (kb / STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dBh = make_desc(st + 2 * A_BYTES), dBl = make_desc(st + 2 * A_BYTES + TILE_BYTES);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {       // accumulator mt = TMEM columns [128 * mt, +128) of the set, A rows [128 * mt, +128)
+                        const uint64_t dAh = make_desc(st + mt * TILE_BYTES), dAl = make_desc(st + A_BYTES + mt * TILE_BYTES);
+                        const uint32_t acc = tmem_base + (uint32_t)(set * ACC_COLS + mt * BN);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K = 8 step inside the swizzled row
+                            umma_tf32(acc, dAl + adv, dBh + adv, idesc, (!first || k > 0) ? 1u : 0u);   // small terms first
+                            umma_tf32(acc, dAh + adv, dBl + adv, idesc, 1u);
+                            umma_tf32(acc, dAh + adv, dBh + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * s);           // frees the smem slot once these MMAs have read it
+                }
+                umma_commit(tmem_full0 + 8 * set);         // chunk complete
             }
-            umma_commit(tmem_full);                    // accumulator complete
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> fp64 -> C.  Warp w may only touch TMEM lanes [32*(w%4), +32) =====
+        // ===== epilogue: TMEM -> registers -> fp64 -> C.  Warp w may only touch TMEM lanes [32*(w%4), +32).
+        // Chunk 0 stores, every later chunk adds to what this same thread stored (fp64, chunk order: the sum the separate
+        // partial-tile reduction of round 1 produced, bit for bit) - the tile stays in L2 between chunks. =====
         const int quad = warp & 3;
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < chunks; ++c) {
+            const int set = c & 1;
+            mbar_wait(tmem_full0 + 8 * set, (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int mc = 0; mc < MT * (BN / 32); ++mc) {
-            const int mt = mc / (BN / 32), c = mc % (BN / 32);
-            const int row = m0 + mt * BM + quad * 32 + lane;
-            double* crow = p.C + (long long)blockIdx.z * p.c_ss + (long long)batch * p.c_sb + (long long)row * p.c_sm;
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < p.M) {
-                const int col0 = n0 + c * 32;
-                if (p.c_sn == 1 && col0 + 31 < p.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+            for (int mc = 0; mc < MT * (BN / 32); ++mc) {
+                const int mt = mc / (BN / 32), cc = mc % (BN / 32);
+                const int row = m0 + mt * BM + quad * 32 + lane;
+                double* crow = p.C + (long long)batch * p.c_sb + (long long)row * p.c_sm;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * ACC_COLS + mt * BN + cc * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+                    const int col0 = n0 + cc * 32;
+                    if (p.c_sn == 1 && col0 + 31 < p.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+                        if (c == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2)
-                        *reinterpret_cast<double2*>(crow + col0 + j) = make_double2((double)__uint_as_float(v[j]), (double)__uint_as_float(v[j + 1]));
-                } else {
+                            for (int j = 0; j < 32; j += 2)
+                                *reinterpret_cast<double2*>(crow + col0 + j) = make_double2((double)__uint_as_float(v[j]), (double)__uint_as_float(v[j + 1]));
+                        } else {
+                            // all 16 loads first: interleaved with the stores they would be serialised (the compiler must assume
+                            // the stores alias the next load: ncu showed one exposed L2 round trip per DADD)
+                            double2 o[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) crow[(long long)(col0 + j) * p.c_sn] = (double)__uint_as_float(v[j]);
+                            for (int j = 0; j < 16; ++j) o[j] = *reinterpret_cast<const double2*>(crow + col0 + 2 * j);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                o[j].x += (double)__uint_as_float(v[2 * j]);
+                                o[j].y += (double)__uint_as_float(v[2 * j + 1]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(crow + col0 + 2 * j) = o[j];
+                        }
+                    } else {
+                        double o[32];                              // (loads first, as above)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = (c > 0 && col0 + j < p.N) ? crow[(long long)(col0 + j) * p.c_sn] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) crow[(long long)(col0 + j) * p.c_sn] = o[j] + (double)__uint_as_float(v[j]);
+                    }
                 }
             }
+            // this set may be overwritten by chunk c + 2
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty0 + 8 * set) : "memory");
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// fp64 (rows x K, MN-contiguous: s_row == 1) -> hi/lo fp32, K-major: a 32 x 32 tile goes through shared memory so that both the
+// fp64 reads (along rows) and the fp32 writes (along k) are coalesced (the element-per-thread kernel below reads such an operand
+// with a stride of a whole row: 8 useful bytes per 32-byte sector).
+__global__ void __launch_bounds__(256)
+split_tf32_t_kernel(const double* __restrict__ src, long long s_k, long long s_b, float* __restrict__ hi, float* __restrict__ lo,
+                    long long rows, long long K, long long Kp) {
+    __shared__ double t[32][33];
+    const long long b = blockIdx.z;
+    const long long r0 = (long long)blockIdx.x * 32, k0 = (long long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    src += b * s_b;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long k = k0 + ty + 8 * j, r = r0 + tx;
+        t[ty + 8 * j][tx] = (k < K && r < rows) ? __ldg(src + k * s_k + r) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long r = r0 + ty + 8 * j, k = k0 + tx;
+        if (r < rows && k < Kp) {
+            const double v = t[tx][ty + 8 * j];
+            uint32_t hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"((float)v));
+            const float h = __uint_as_float(hb);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"((float)(v - (double)h)));
+            const long long o = (b * rows + r) * Kp + k;
+            hi[o] = h;
+            lo[o] = __uint_as_float(lb);
+        }
     }
 }
 
@@ -302,8 +385,14 @@ int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
     if (e != cudaSuccess) return set_error("gemm_tf32x3: workspace allocation failed: %s", cudaGetErrorString(e));
     float *a_hi = ws, *a_lo = ws + a_elems, *b_hi = ws + 2 * a_elems, *b_lo = ws + 2 * a_elems + b_elems;
     auto grid_for = [](size_t n) { size_t g = (n + 255) / 256; return (unsigned)(g > 148 * 32 ? 148 * 32 : g); };
-    split_tf32_kernel<<<grid_for(a_elems), 256, 0, st>>>(d->A, d->a_sm, d->a_sk, d->a_sb, a_hi, a_lo, M, K, Kp, batch);
-    split_tf32_kernel<<<grid_for(b_elems), 256, 0, st>>>(d->B, d->b_sn, d->b_sk, d->b_sb, b_hi, b_lo, N, K, Kp, batch);
+    auto split = [&](const double* src, long long s_row, long long s_k, long long s_b, float* hi, float* lo, long long rows, size_t elems) {
+        if (s_row == 1 && s_k != 1 && rows >= 32 && K >= 32 && (rows + 31) / 32 < (1LL << 31) && (Kp + 31) / 32 <= 65535)
+            split_tf32_t_kernel<<<dim3((unsigned)((rows + 31) / 32), (unsigned)((Kp + 31) / 32), (unsigned)batch), 256, 0, st>>>(src, s_k, s_b, hi, lo, rows, K, Kp);
+        else
+            split_tf32_kernel<<<grid_for(elems), 256, 0, st>>>(src, s_row, s_k, s_b, hi, lo, rows, K, Kp, batch);
+    };
+    split(d->A, d->a_sm, d->a_sk, d->a_sb, a_hi, a_lo, M, a_elems);
+    split(d->B, d->b_sn, d->b_sk, d->b_sb, b_hi, b_lo, N, b_elems);
     count_launch(2);
     // 256-row CTA tiles (two accumulators sharing the B tiles) when there are enough of them to fill the GPU; ADB_TF32_MT=1|2 overrides
     static int mt_pref = -1;
@@ -324,46 +413,25 @@ int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
         attr_set = true;
     }
     // The tensor core accumulates in fp32 with truncation, so the error of one accumulation chain grows ~linearly
-    // with its length (measured 1.4e-5 at K = 2048, 3.3e-5 at 4096).  K is therefore processed in chunks of <= 2048
-    // by separate CTAs (blockIdx.z) whose fp64 partial tiles are summed in fp64 by the reduction kernel.
+    // with its length (measured 1.4e-5 at K = 2048, 3.3e-5 at 4096).  K is therefore processed in chunks of <= 2048: each chunk is
+    // its own fp32 chain in TMEM, and the chunks are added in fp64 by the epilogue warps (chunk c + 1 accumulates in the second
+    // TMEM set while chunk c is drained) - round 1 wrote every chunk's tile to a workspace and summed them in a second kernel.
     const int total_kb = (int)((K + BK - 1) / BK);
     const int max_kb = 2048 / BK;
-    int splits = (total_kb + max_kb - 1) / max_kb;
-    const int kb_per_split = (total_kb + splits - 1) / splits;
-    splits = (total_kb + kb_per_split - 1) / kb_per_split;
-    double* ws_c = nullptr;
-    const long long Np = (N + 1) & ~1LL;
-    if (splits > 1) {
-        e = cudaMallocAsync(reinterpret_cast<void**>(&ws_c), (size_t)splits * batch * M * Np * sizeof(double), st);
-        if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm_tf32x3: split workspace allocation failed: %s", cudaGetErrorString(e)); }
-    }
+    const int chunks = (total_kb + max_kb - 1) / max_kb;
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.tiles_m = (int)((M + BM * MT - 1) / (BM * MT)); p.tiles_n = (int)((N + BN - 1) / BN);
-    p.kb_per_split = kb_per_split; p._pad = 0;
-    if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
-    else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
-    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
+    p.kb_per_chunk = (total_kb + chunks - 1) / chunks; p._pad = 0;
+    p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb;
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, 1u);
     if (MT == 2) gemm_tf32x3_kernel<2><<<grid, THREADS, Cfg<2>::SMEM, st>>>(tAh, tAl, tBh, tBl, p);
     else gemm_tf32x3_kernel<1><<<grid, THREADS, Cfg<1>::SMEM, st>>>(tAh, tAl, tBh, tBl, p);
     e = cudaGetLastError();
     cudaFreeAsync(ws, st);
-    if (e != cudaSuccess) { if (ws_c) cudaFreeAsync(ws_c, st); return set_error("gemm_tf32x3 launch failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return set_error("gemm_tf32x3 launch failed: %s", cudaGetErrorString(e));
     count_launch();
-    int rc = 0;
-    if (splits > 1) {
-        ReduceSpec S;
-        memset(&S, 0, sizeof S);
-        S.n_ops = 1; S.n_o = 3; S.n_r = 1; S.group = 1;
-        S.odim[0] = N; S.odim[1] = M; S.odim[2] = batch;
-        S.out_s[0] = d->c_sn; S.out_s[1] = d->c_sm; S.out_s[2] = d->c_sb;
-        S.op_os[0][0] = 1; S.op_os[0][1] = Np; S.op_os[0][2] = M * Np;
-        S.rdim[0] = splits; S.op_rs[0][0] = (long long)batch * M * Np;
-        S.op[0] = ws_c; S.out = d->C;
-        rc = reduce_run(S, st);
-        cudaFreeAsync(ws_c, st);
-    }
-    return rc;
+    return 0;
 }
 
 }  // namespace adb

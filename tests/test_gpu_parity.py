@@ -455,6 +455,37 @@ def test_tf32x3_precision_mode(ad):
     check((ad.Variable(a, name="a") @ ad.Variable(b, name="b"))(), a @ b)      # back to fp64 outside the context
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,k,n", [(4096, 4096, 4096), (1024, 4097, 1536), (640, 8192, 384), (257, 2049, 130)])
+def test_tf32x3_large_full_matrix(m, k, n, ad):
+    """3xTF32 at sizes with several accumulation chunks (K > 2048: the chunks are added in fp64 by the epilogue warps), a ragged
+    K = 4097 and odd extents: forward and BOTH gradients compared over the full matrices against the FP64 DMMA path on the device
+    (itself pinned to the oracle at the sizes numpy finishes in seconds).  Bar 1e-4 (north_star), expected ~1e-6."""
+    import torch
+    rng = np.random.default_rng(m + k + n)
+    a = ad.to_device(rng.standard_normal((m, k))); b = ad.to_device(rng.standard_normal((k, n)))
+    w = ad.to_device(rng.standard_normal((m, n)))
+
+    def run():
+        A, B, W = ad.Variable(a, name="a"), ad.Variable(b, name="b"), ad.Variable(w, name="w")
+        e = ad.Einsum("ij,jk->ik", A, B)
+        loss = ad.Einsum("ik,ik->", e, W)                      # non-trivial upstream gradient
+        return [x.eval_device() for x in [e] + ad.grad(loss, [A, B])]
+
+    ref = run()
+    with ad.precision("tf32x3"):
+        got = run()
+        again = run()
+    def view(d):                                              # (pitched rows: compare the elements, not the padding)
+        return torch.as_strided(d.base, tuple(d.shape), tuple(d.strides), d.offset)
+    for g, r, g2 in zip(got, ref, again):
+        tg, tr = view(g), view(r)
+        err = float((tg - tr).abs().max() / tr.abs().max())
+        assert err <= 1e-4, err
+        assert err > 1e-13, "tf32x3 mode did not change the arithmetic"
+        assert torch.equal(tg, view(g2)), "tf32x3 result differs from run to run"
+
+
 # ------------------------------------------------------------------------------------- static programs vs interpreter
 @pytest.mark.gpu
 def test_catalogued_programs_match_interpreter_bitwise():

@@ -133,10 +133,11 @@ static int run_case(const Case& c, bool time_it, int reps) {
 }
 
 // ---- 3xTF32 tcgen05 variant: same contract, tolerance 1e-4 (north_star), expected ~1e-7
-static int run_tf32(long long M, long long N, long long K, long long nb, int a_kc, int b_kc, bool time_it) {
+static int run_tf32(long long M, long long N, long long K, long long nb, int a_kc, int b_kc, bool time_it, bool dense = false) {
     adb_gemm_desc d; memset(&d, 0, sizeof d);
     d.M = M; d.N = N; d.K = K; d.batch = nb;
     long long a_ld = a_kc ? K + 1 : M + 3, b_ld = b_kc ? K + 1 : N + 3, c_ld = N + 1;   // odd pitches on purpose: any strides are legal
+    if (dense) { a_ld = a_kc ? K : M; b_ld = b_kc ? K : N; c_ld = N; }                   // (what the einsum path passes: dense, aligned rows)
     long long a_elems = (a_kc ? M : K) * a_ld, b_elems = (b_kc ? N : K) * b_ld;
     if (a_kc) { d.a_sm = a_ld; d.a_sk = 1; } else { d.a_sm = 1; d.a_sk = a_ld; }
     if (b_kc) { d.b_sn = b_ld; d.b_sk = 1; } else { d.b_sn = 1; d.b_sk = b_ld; }
@@ -184,13 +185,22 @@ int main(int argc, char** argv) {
         run_case(Case{atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoll(argv[5]), atoi(argv[6]), atoi(argv[7]), 0, atoi(argv[8])}, true, 2);
         return 0;
     }
+    if (argc > 2 && !strcmp(argv[1], "tf32one")) {         // one timed 3xTF32 case (for ncu): tf32one N [b_kc]
+        const long long n = atoll(argv[2]);
+        run_tf32(n, n, n, 1, 1, argc > 3 ? atoi(argv[3]) : 0, true, true);
+        return 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "tf32")) {
         int fails = 0;
-        long long shapes[][4] = {{128, 128, 32, 1}, {128, 128, 256, 1}, {256, 384, 100, 1}, {200, 136, 77, 1}, {257, 129, 50, 3}, {1000, 520, 333, 2}, {64, 64, 1024, 1}};
+        long long shapes[][4] = {{128, 128, 32, 1}, {128, 128, 256, 1}, {256, 384, 100, 1}, {200, 136, 77, 1}, {257, 129, 50, 3}, {1000, 520, 333, 2}, {64, 64, 1024, 1},
+                                 {256, 256, 4100, 1}, {300, 200, 8200, 2}, {1024, 1536, 4097, 1}, {4097, 1536, 1024, 1}, {2560, 2048, 6200, 1}};   // K > 2048: several fp32 chains
         for (auto& s : shapes) for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) fails += run_tf32(s[0], s[1], s[2], s[3], a, b, false);
         printf("tf32x3 correctness: %d failing cases\n", fails);
-        for (long long n : {2048ll, 4096ll, 8192ll}) run_tf32(n, n, n, 1, 1, 0, true);
-        run_tf32(1024, 1024, 1024, 64, 1, 0, true);
+        for (long long n : {2048ll, 4096ll, 8192ll}) run_tf32(n, n, n, 1, 1, 0, true, true);
+        run_tf32(8192, 8192, 8192, 1, 1, 1, true, true);
+        run_tf32(8192, 8192, 8192, 1, 0, 0, true, true);
+        run_tf32(1024, 1024, 1024, 64, 1, 0, true, true);
+        run_tf32(8192, 8192, 8192, 1, 1, 0, true, false);       // odd pitches: element-wise epilogue
         return fails ? 1 : 0;
     }
     int fails = 0;
