@@ -127,6 +127,18 @@ def run_gpu(args):
     ad.init(local)
     dist = None
     if world > 1:
+        # one slice of the allowed host cores per rank: the upload / download staging of N ranks shares one NUMA node on this box
+        # class (topology: all GPUs report CPU affinity 0-31, node 0), so the ranks are at least kept off each other's cores
+        try:
+            if os.environ.get("ADB_BENCH_BIND", "1") == "0":
+                raise OSError
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[(local * per) % len(cores):][:per]
+            if mine:
+                os.sched_setaffinity(0, mine)
+        except (AttributeError, OSError):
+            pass
         import torch.distributed as dist
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
@@ -243,6 +255,9 @@ def run_gpu(args):
             d2h += 8 * (out_elems + int(np.prod(shapes[0])) + int(np.prod(shapes[1])))     # E, dA, dB
         e2e = {"value": round(world * flops / (ems * 1e-3) / 1e12, 4), "unit": "TFLOP/s", "ms_per_step": round(ems, 3), "steps": k,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "h2d_gbs_per_rank": round(h2d / (ems * 1e-3) / 1e9, 1), "d2h_gbs_per_rank": round(d2h / (ems * 1e-3) / 1e9, 1),
+               "host_link_gbs_all_ranks": round(world * (h2d + d2h) / (ems * 1e-3) / 1e9, 1),
+               "host_link_ceiling": "tools/probe_host_link.py, profiles/r02_host_link.md: aggregate pinned-copy GB/s per direction at N = 1, 2, 4, 8 on this box class",
                "api": "ad.Variable(pinned ndarray) -> ad.Einsum / ad.grad -> ad.eval_many(nodes) returns host ndarrays "
                       "(== [n() for n in nodes]; H2D, kernels and D2H pipelined on three streams)"}
 

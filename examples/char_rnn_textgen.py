@@ -2,7 +2,7 @@
 reference's examples/char_rnn.py, on a small built-in corpus.  The graph is rebuilt every step, as in the reference;
 from the third step on the structure-keyed launch tape replays it.
 
-    python examples/char_rnn_textgen.py [--steps 200] [--hidden 100] [--unroll 20]
+    python examples/char_rnn_textgen.py [--steps 200] [--hidden 100] [--unroll 20] [--corpus some_text.txt]
 """
 import argparse
 import os
@@ -18,9 +18,10 @@ ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--hidden", type=int, default=100)
 ap.add_argument("--unroll", type=int, default=20)
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--corpus", default=None, help="a text file to train on (e.g. the reference's examples/sample_text_for_generation.txt); default: a built-in pangram corpus")
 args = ap.parse_args()
 
-corpus = ("the quick brown fox jumps over the lazy dog. pack my box with five dozen liquor jugs. "
+corpus = open(args.corpus, encoding="utf-8", errors="ignore").read() if args.corpus else ("the quick brown fox jumps over the lazy dog. pack my box with five dozen liquor jugs. "
           "how vexingly quick daft zebras jump. sphinx of black quartz, judge my vow. ") * 40
 chars = sorted(set(corpus))
 index = {c: i for i, c in enumerate(chars)}
