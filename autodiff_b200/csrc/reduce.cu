@@ -976,7 +976,8 @@ int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb
     const bool quad_ok = labels->stride[1] == 1 && logits->stride[1] == 1 && aligned32(labels->ptr) && aligned32(logits->ptr) &&
                          labels->stride[0] % 4 == 0 && logits->stride[0] % 4 == 0;
     if (quad_ok && sce_ring_enabled()) {
-        const int r = softmax_ce_ring_try(labels, logits, out, flag, st);     // persistent ring kernel (softmax_ce_ring.cu)
+        int r = softmax_ce_ring_try(labels, logits, out, flag, st);           // persistent ring kernels (softmax_ce_ring.cu)
+        if (r < 0) r = softmax_ce_ring_narrow_try(labels, logits, out, flag, st);
         if (r >= 0) return r;
     }
     static int warp_rows = -1;                    // ADB_SCE_WARP=0: the round-1 dispatch (A/B measurements)

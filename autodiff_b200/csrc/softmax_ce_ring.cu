@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "adb_internal.h"
 #include "adb_math.cuh"
@@ -196,7 +197,137 @@ cudaError_t launch_ring(const adb_tensor* labels, const adb_tensor* logits, cons
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------- narrow rows (128 < cols <= 512)
+// The same decoupling for rows of 1-4 KB: one persistent CTA per SM, every WARP an independent consumer that owns SPW slots of
+// the ring, a slot = one row (logits + labels, two bulk copies on the slot's mbarrier).  The warp drains a slot into registers
+// (K quads per lane), its lane 0 re-arms the slot with the warp's next row, then the dependent chain (max -> exp -> sum -> log)
+// runs out of registers while WARPS x SPW rows per SM keep streaming in.  The register-only warp kernel (reduce.cu) alternates
+// load and FP64 phases with 16 warps per SM: 0.71 of the HBM roof at 512 columns.  Arithmetic: the warp kernel's.
+template <int K>
+__global__ void __launch_bounds__(512, 1)
+softmax_ce_ring_narrow_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits, long long z_sr,
+                              double* __restrict__ out, long long o_s, long long rows, unsigned cols, unsigned half_bytes, unsigned copy_bytes,
+                              int spw, int* __restrict__ flag) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long bars[64];
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < warps * spw; ++s) bar_init(s_u32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const long long first = (long long)blockIdx.x * warps + w, step = (long long)gridDim.x * warps;
+    const long long mine = first < rows ? (rows - first + step - 1) / step : 0;
+    const uint32_t slot_bytes = 2u * half_bytes;
+    unsigned char* const wring = ring + (size_t)w * spw * slot_bytes;
+    const uint32_t wbar = s_u32(bars + w * spw);
+    auto arm = [&](long long k) {                      // lane 0: start the copies of the warp's k-th row
+        const int s = (int)(k % spw);
+        const long long r = first + k * step;
+        const uint32_t dst = s_u32(wring) + s * slot_bytes;
+        bar_expect_tx(wbar + 8 * s, 2 * copy_bytes);
+        bulk_load(dst, logits + r * z_sr, copy_bytes, wbar + 8 * s);
+        bulk_load(dst + half_bytes, labels + r * l_sr, copy_bytes, wbar + 8 * s);
+    };
+    if (lane == 0)
+        for (long long k = 0; k < spw && k < mine; ++k) arm(k);
+    for (long long k = 0; k < mine; ++k) {
+        const int s = (int)(k % spw);
+        bar_wait(wbar + 8 * s, (uint32_t)(k / spw) & 1u);
+        const double2* zs = reinterpret_cast<const double2*>(wring + (size_t)s * slot_bytes);
+        const double2* ls = reinterpret_cast<const double2*>(wring + (size_t)s * slot_bytes + half_bytes);
+        double z[4 * K];
+        double lsum = 0.0, dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 2 * K; ++q) {              // 16-byte pairs, lane-interleaved: conflict-free LDS.128
+            const unsigned c = 2u * (q * 32u + lane);
+            double2 zv = make_double2(-INFINITY, -INFINITY), lv = make_double2(0.0, 0.0);
+            if (c < cols) { zv = zs[q * 32 + lane]; lv = ls[q * 32 + lane]; }
+            if (c + 1 >= cols) { zv.y = -INFINITY; lv.y = 0.0; }      // odd width: the pair's second half is row padding
+            z[2 * q] = zv.x; z[2 * q + 1] = zv.y;
+            if (c < cols) dot += lv.x * zv.x;
+            if (c + 1 < cols) dot += lv.y * zv.y;
+            lsum += lv.x;
+            lsum += lv.y;
+        }
+        __syncwarp();                                  // the slot is drained
+        if (lane == 0 && k + spw < mine) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            arm(k + spw);
+        }
+        double m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4 * K; ++e) m = fmax(m, z[e]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        const double mm = m == -INFINITY ? 0.0 : m;    // (fmax skips NaN, exp_nonpos does not: a NaN logit makes `se` NaN)
+        double se = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4 * K; ++e) se += exp_nonpos(z[e] - mm);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, off);
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+            dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        }
+        if (lane == 0) {
+            if (m == -INFINITY) se = NAN;              // a row of -inf: numpy computes exp(-inf - -inf) = nan
+            const double lse = m + log(se);
+            out[(first + k * step) * o_s] = -(dot - lse * lsum);
+            if (!(fabs(lsum - 1.0) <= 1e-8 + 1e-5)) atomicOr(flag, 1);
+        }
+    }
+}
+
+template <int K>
+cudaError_t launch_ring_narrow(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st, unsigned grid) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(softmax_ce_ring_narrow_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCE_RING_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const unsigned cols = (unsigned)logits->shape[1];
+    const unsigned copy_bytes = (cols + 1) / 2 * 16, half_bytes = (copy_bytes + 127) / 128 * 128;
+    // as many (warp, slot) pairs as fit the 192 KB ring: 12 warps x 2 slots at 512 columns, 16 x 3 at 256, 16 x 4 below
+    int warps = 16, spw = (int)(SCE_RING_BYTES / (16 * 2 * half_bytes));
+    if (spw < 2) { warps = 12; spw = (int)(SCE_RING_BYTES / (12 * 2 * half_bytes)); }
+    if (spw > 4) spw = 4;
+    if (spw < 1) return cudaErrorInvalidValue;
+    const int smem = warps * spw * 2 * (int)half_bytes;
+    softmax_ce_ring_narrow_kernel<K><<<grid, warps * 32, smem, st>>>(
+        static_cast<const double*>(labels->ptr), labels->stride[0], static_cast<const double*>(logits->ptr), logits->stride[0],
+        static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], cols, half_bytes, copy_bytes, spw, flag);
+    return cudaGetLastError();
+}
+
 }  // namespace
+
+// Narrow rows through the ring: 0 = launched, 1 = error, -1 = not applicable.  Same preconditions as softmax_ce_ring_try.
+int softmax_ce_ring_narrow_try(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st) {
+    const long long rows = logits->shape[0], cols = logits->shape[1];
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    static int lo = -1;                            // ADB_SCE_NARROW_RING=0 disables; =N sets the smallest width (A/B measurements)
+    if (lo < 0) { const char* e = getenv("ADB_SCE_NARROW_RING"); lo = e ? atoi(e) : 257; if (e && lo <= 0) lo = 1 << 30; }
+    // (measured, profiles/r02_softmax_ce_warp.log: ring / register-only warp kernel = 0.76 / 0.70 of the HBM roof at 512 columns,
+    // 0.64 / 0.55 at 384, but 0.65 / 0.73 at 256 and 0.52 / 0.59 at 200: 2 KB copies no longer amortise the slot round trip)
+    if (cols < lo || cols > 512 || rows < 64LL * sms) return -1;      // a persistent grid needs many rows per warp
+    const unsigned grid = (unsigned)sms;
+    cudaError_t e;
+    if (cols <= 128) e = launch_ring_narrow<1>(labels, logits, out, flag, st, grid);
+    else if (cols <= 256) e = launch_ring_narrow<2>(labels, logits, out, flag, st, grid);
+    else e = launch_ring_narrow<4>(labels, logits, out, flag, st, grid);
+    if (e != cudaSuccess) return set_error("softmax_ce narrow ring launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return 0;
+}
 
 // Returns 0 = launched, 1 = error (set_error called), -1 = not applicable (the caller uses the register-resident kernels).
 // Preconditions checked by the caller: 2-D, unit column stride, 32-byte aligned bases, row strides multiples of 4.

@@ -537,6 +537,50 @@ def test_softmax_ce_wide_rows(cols, ad):
         ad.SoftmaxCEWithLogits(labels=ad.Variable(bad, name="l"), logits=ad.Variable(z, name="z"))()
 
 
+@pytest.mark.parametrize("cols", [8, 64, 100, 128, 130, 200, 256, 260, 384, 511, 512])
+@pytest.mark.parametrize("rows", [300, 64 * 148 + 77])
+def test_softmax_ce_narrow_rows(rows, cols, ad):
+    """Rows of <= 512 columns: the warp-per-row register kernel (csrc/reduce.cu: softmax_ce_warp_kernel) and, from 64 rows per SM
+    and 129 columns on, the narrow bulk-copy ring (csrc/softmax_ce_ring.cu: softmax_ce_ring_narrow_kernel) - against the oracle,
+    against each other (ADB_SCE_RING=0), NaN / -inf / +inf rows, label validation, a pitched window of a wider array."""
+    rng = np.random.default_rng(rows + cols)
+    z = rng.standard_normal((rows, cols)) * 4
+    lab = rng.random((rows, cols)); lab /= lab.sum(1, keepdims=True)
+
+    def run(zz, ll):
+        return ad.SoftmaxCEWithLogits(labels=ad.Variable(ll, name="l"), logits=ad.Variable(zz, name="z"))()
+    got = run(z, lab)
+    ref = onp.SoftmaxCEWithLogits(labels=onp.Variable(lab, name="l"), logits=onp.Variable(z, name="z"))()
+    assert got.shape == ref.shape
+    check(got, ref)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+    os.environ["ADB_SCE_RING"] = "0"
+    try:
+        other = run(z, lab)
+    finally:
+        del os.environ["ADB_SCE_RING"]
+    check(got, other)
+    wide_z = rng.standard_normal((rows, cols + 12)); wide_l = rng.random((rows, cols + 12))
+    wide_l[:, 4:4 + cols] /= wide_l[:, 4:4 + cols].sum(1, keepdims=True)
+    zd, ld = ad.to_device(wide_z), ad.to_device(wide_l)
+    got_v = run(zd.getitem((slice(None), slice(4, 4 + cols))), ld.getitem((slice(None), slice(4, 4 + cols))))
+    ref_v = onp.SoftmaxCEWithLogits(labels=onp.Variable(wide_l[:, 4:4 + cols], name="l"), logits=onp.Variable(wide_z[:, 4:4 + cols], name="z"))()
+    check(got_v, ref_v)
+    z[5, 7] = np.nan
+    z[9, :] = -np.inf
+    z[11, 3] = np.inf
+    z[13, :] = -np.inf; z[13, 5] = np.nan; z[13, cols - 1] = 1.0
+    z[rows - 2, cols - 1] = np.nan
+    got = run(z, lab)
+    assert all(np.isnan(got[r]) for r in (5, 9, 11, 13, rows - 2))
+    assert not np.isnan(got[4]) and not np.isnan(got[rows - 1])
+    keep = np.ones(rows, bool); keep[[5, 9, 11, 13, rows - 2]] = False
+    check(got[keep], ref[keep])
+    bad = lab.copy(); bad[rows - 1] *= 1.01
+    with pytest.raises(ValueError, match="Labels must be a valid probability distribution!"):
+        run(z, bad)
+
+
 @pytest.mark.parametrize("cols", [1024, 2048, 2049, 2500, 3001, 3072, 3073, 4095, 4096, 4097, 4100, 5001, 6144, 8191, 8192])
 def test_softmax_ce_ring_rows(cols, ad):
     """Persistent bulk-copy ring kernel (csrc/softmax_ce_ring.cu: rows >= 4 per SM, 2048 < cols <= 8192; beyond 4096 columns a
