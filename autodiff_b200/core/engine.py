@@ -321,17 +321,10 @@ def eval_many(tops):
     if tr is not None:
         tr.append(("start", start))
     info, leaf_event, keep = {}, {}, []
+    wanted = {}                      # id(output) -> its host leaves still to upload
     for x in todo:
         uploads, leaf_ids, interior, flops = _survey(x)
-        for leaf, value in uploads:
-            if leaf._dev is None:
-                leaf._dev, staged = to_device_async(value, h2d)
-                keep.append(staged)
-                ev = t.cuda.Event(enable_timing=tr is not None)
-                ev.record(h2d)
-                leaf_event[id(leaf)] = ev
-                if tr is not None:
-                    tr.append(("uploaded %s %s" % (leaf.name, value.shape), ev))
+        wanted[id(x)] = uploads
         info[id(x)] = (leaf_ids, interior, flops)
     # 2. independent jobs = connected components over shared interior nodes
     comp = list(range(len(todo)))
@@ -350,16 +343,44 @@ def eval_many(tops):
     groups = {}
     for i, x in enumerate(todo):
         groups.setdefault(find(i), []).append(x)
-    heaviest = max([sum(info[id(x)][2] for x in g) for g in groups.values()] or [0.0])
+    weight = {k: sum(info[id(x)][2] for x in g) for k, g in groups.items()}
+    heaviest = max(list(weight.values()) or [0.0])
     plans = {}
     stream_of = {}
-    for g in groups.values():
+    for k, g in groups.items():
         plan = _plan(g)
         # light = a job several times cheaper than the heaviest one, when that one is long enough to be worth dodging
-        is_light = heaviest >= HEAVY_FLOPS and len(groups) > 1 and sum(info[id(x)][2] for x in g) < 0.3 * heaviest
+        is_light = heaviest >= HEAVY_FLOPS and len(groups) > 1 and weight[k] < 0.3 * heaviest
         for x in g:
             plans[id(x)] = plan
             stream_of[id(x)] = light if is_light else main
+    # upload order: leaves too small to matter first (an output that needs nothing else - the outer-product gradient of
+    # 'ijkl,jl->ik' needs only the 128 x 128 operand - can start, and its result can start travelling back, at once), then
+    # the leaves of the HEAVIEST job (its kernels are the long pole of the pass), then the rest in the order given
+    order_key = {}
+    for i, x in enumerate(todo):
+        w = weight[find(i)]
+        for leaf, value in wanted[id(x)]:
+            key = (0 if value.nbytes < PIPELINE_MIN_BYTES else (1 if w >= heaviest else 2), len(order_key))
+            order_key.setdefault(id(leaf), (key, leaf, value))
+    position = {}                    # id(leaf) -> bytes queued on the upload stream up to and including this leaf
+    queued = 0
+    for key, leaf, value in sorted(order_key.values(), key=lambda e: e[0]):
+        if leaf._dev is None:
+            leaf._dev, staged = to_device_async(value, h2d)
+            keep.append(staged)
+            ev = t.cuda.Event(enable_timing=tr is not None)
+            ev.record(h2d)
+            leaf_event[id(leaf)] = ev
+            queued += value.nbytes
+            position[id(leaf)] = queued
+            if tr is not None:
+                tr.append(("uploaded %s %s" % (leaf.name, value.shape), ev))
+    # issue order: an output whose leaves arrive earlier goes first (stable: the caller's order among equals), so that on each
+    # stream nothing ready waits behind an output whose operand is still on the wire
+    ready_at = {id(x): max([position.get(lid, 0) for lid in info[id(x)][0]] or [0]) for x in todo}
+    rank_of = {id(x): i for i, x in enumerate(pending)}
+    pending = sorted(pending, key=lambda x: (ready_at.get(id(x), 0), rank_of[id(x)]))
     # 3. kernels per output on its job's stream; each result's download is queued behind its own kernels only
     results = {}
     used_light = False
