@@ -291,6 +291,227 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
 }
 
+// ----------------------------------------------------------------------------- CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute a 256 x 256 tile together: each loads ITS 128 rows of A (hi, lo) and ITS 128 of the 256
+// B rows (hi, lo) - 64 KiB per k-block and CTA instead of 96 KiB for the same 6.3 MFLOP, so three stages fit and the operand bytes
+// per flop drop by a third (the single-CTA kernel is bound by operand delivery).  All eight TMA loads of a stage
+// signal the LEADER's full barrier (`cp.async.bulk.tensor...cta_group::2`, barrier address with the peer bit cleared); the leader's
+// MMA thread issues `tcgen05.mma.cta_group::2` (M = 256, N = 256, K = 8: each CTA's tensor core produces its 128 rows from its own
+// A tile and both CTAs' B halves) and `tcgen05.commit...multicast::cluster` releases the smem slot / hands over the accumulator
+// set in BOTH CTAs.  Each CTA's epilogue warps drain their own 128 TMEM lanes x 256 columns and arrive on the leader's
+// tmem_empty barrier.  Chains of <= 2048 and the fp64 accumulation in C as in the single-CTA kernel.
+struct Cfg2 {
+    static constexpr int STAGES = 3;
+    static constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // A_hi, A_lo, B_hi, B_lo: 128 rows each
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 128;
+    static constexpr int BN2 = 256;                               // columns of the pair's tile = columns of one accumulator set
+    static constexpr int TMEM_COLS = 2 * BN2;
+};
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;                   // shared::cluster address of the same offset in CTA rank 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const Params p) {
+    constexpr int STAGES = Cfg2::STAGES, STAGE_BYTES = Cfg2::STAGE_BYTES, BN2 = Cfg2::BN2, TMEM_COLS = Cfg2::TMEM_COLS;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars);                            // used in the leader only
+    const uint32_t empty0 = smem_u32(bars + STAGES);
+    const uint32_t tmem_full0 = smem_u32(bars + 2 * STAGES);
+    const uint32_t tmem_empty0 = smem_u32(bars + 2 * STAGES + 2);     // used in the leader only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int GROUP = 8;                                              // grouped rasterisation over the pair tiles
+    const int tile = blockIdx.x >> 1;
+    const int group_size = GROUP * p.tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(p.tiles_m - first_m, GROUP);
+    const int tm = first_m + (tile % group_size) % gm, tn = (tile % group_size) / gm;
+    const int m0 = tm * 256 + (int)rank * BM;                         // this CTA's rows of A and C
+    const int n0 = tn * BN2;
+    const int nb0 = n0 + (int)rank * BN;                              // this CTA's half of the B rows
+    const int batch = blockIdx.y;
+    const int total_kb = (p.K + BK - 1) / BK;
+    const int chunks = (total_kb + p.kb_per_chunk - 1) / p.kb_per_chunk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 2);              // the leader's arrive.expect_tx + the peer's arrive
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full0 + 8 * s, 1);
+            mbar_init(tmem_empty0 + 8 * s, 8);        // lane 0 of the four epilogue warps of BOTH CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                               // both CTAs' barriers initialised and TMEM allocated before anyone signals
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const uint32_t fb = (full0 + 8 * s) & PEER_BIT_MASK;      // the leader's barrier
+                if (leader) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                const int k0 = kb * BK;
+                tma_load_3d_2sm(st, &tmAh, fb, k0, m0, batch);
+                tma_load_3d_2sm(st + TILE_BYTES, &tmAl, fb, k0, m0, batch);
+                tma_load_3d_2sm(st + 2 * TILE_BYTES, &tmBh, fb, k0, nb0, batch);
+                tma_load_3d_2sm(st + 3 * TILE_BYTES, &tmBl, fb, k0, nb0, batch);
+                if (!leader) mbar_arrive_cluster(fb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's thread drives both tensor cores =====
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            int kb = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int set = c & 1;
+                if (c >= 2) {
+                    mbar_wait(tmem_empty0 + 8 * set, ((c >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const int kb_end = min(kb + p.kb_per_chunk, total_kb);
+                const uint32_t acc = tmem_base + (uint32_t)(set * BN2);
+                for (bool first = true; kb < kb_end; ++kb, first = false) {
+                    const int s = kb % STAGES;
+                    const uint32_t ph = (kb / STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dAh = make_desc(st), dAl = make_desc(st + TILE_BYTES);
+                    const uint64_t dBh = make_desc(st + 2 * TILE_BYTES), dBl = make_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                        umma_tf32_2sm(acc, dAl + adv, dBh + adv, idesc, (!first || k > 0) ? 1u : 0u);   // small terms first
+                        umma_tf32_2sm(acc, dAh + adv, dBl + adv, idesc, 1u);
+                        umma_tf32_2sm(acc, dAh + adv, dBh + adv, idesc, 1u);
+                    }
+                    umma_commit_2sm(empty0 + 8 * s);
+                }
+                umma_commit_2sm(tmem_full0 + 8 * set);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): own 128 TMEM lanes x 256 columns -> fp64 -> C =====
+        const int quad = warp & 3;
+        const int row = m0 + quad * 32 + lane;
+        double* crow = p.C + (long long)batch * p.c_sb + (long long)row * p.c_sm;
+        for (int c = 0; c < chunks; ++c) {
+            const int set = c & 1;
+            mbar_wait(tmem_full0 + 8 * set, (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int cc = 0; cc < BN2 / 32; ++cc) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * BN2 + cc * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+                    const int col0 = n0 + cc * 32;
+                    if (p.c_sn == 1 && col0 + 31 < p.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+                        if (c == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2)
+                                *reinterpret_cast<double2*>(crow + col0 + j) = make_double2((double)__uint_as_float(v[j]), (double)__uint_as_float(v[j + 1]));
+                        } else {
+                            double2 o[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = *reinterpret_cast<const double2*>(crow + col0 + 2 * j);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                o[j].x += (double)__uint_as_float(v[2 * j]);
+                                o[j].y += (double)__uint_as_float(v[2 * j + 1]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(crow + col0 + 2 * j) = o[j];
+                        }
+                    } else {
+                        double o[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = (c > 0 && col0 + j < p.N) ? crow[(long long)(col0 + j) * p.c_sn] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) crow[(long long)(col0 + j) * p.c_sn] = o[j] + (double)__uint_as_float(v[j]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster((tmem_empty0 + 8 * set) & PEER_BIT_MASK);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                               // the peer's smem / barriers / TMEM are in use until both CTAs are here
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 // fp64 (rows x K, MN-contiguous: s_row == 1) -> hi/lo fp32, K-major: a 32 x 32 tile goes through shared memory so that both the
 // fp64 reads (along rows) and the fp32 writes (along k) are coalesced (the element-per-thread kernel below reads such an operand
 // with a stride of a whole row: 8 useful bytes per 32-byte sector).
@@ -399,6 +620,38 @@ int gemm_tf32x3(const adb_gemm_desc* d, cudaStream_t st) {
     if (mt_pref < 0) { const char* ev = getenv("ADB_TF32_MT"); mt_pref = ev ? atoi(ev) : 0; }
     const long long tiles256 = ((M + 255) / 256) * ((N + BN - 1) / BN) * batch;
     const int MT = mt_pref == 1 ? 1 : (mt_pref == 2 ? 2 : (tiles256 >= 148 ? 2 : 1));
+    // CTA-pair kernel (256 x 256 tile per cluster of two) when there are enough pair tiles to fill the 74 TPCs; ADB_TF32_2CTA=0 never, =2 always
+    const char* pair_env = getenv("ADB_TF32_2CTA");
+    const int pair_pref = pair_env ? atoi(pair_env) : 1;
+    const long long pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    const bool use_pair = pair_pref == 2 || (pair_pref == 1 && mt_pref == 0 && pair_tiles * batch >= 74);
+    if (use_pair) {
+        CUtensorMap pAh, pAl, pBh, pBl;
+        if (!make_tmap_f32(&pAh, a_hi, K, M, batch, Kp, BM) || !make_tmap_f32(&pAl, a_lo, K, M, batch, Kp, BM) ||
+            !make_tmap_f32(&pBh, b_hi, K, N, batch, Kp, BN) || !make_tmap_f32(&pBl, b_lo, K, N, batch, Kp, BN)) {
+            cudaFreeAsync(ws, st);
+            return set_error("gemm_tf32x3: cuTensorMapEncodeTiled rejected the operands");
+        }
+        static bool pair_attr = false;
+        if (!pair_attr) {
+            e = cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM);
+            if (e != cudaSuccess) { cudaFreeAsync(ws, st); return set_error("gemm_tf32x3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
+            pair_attr = true;
+        }
+        const int total_kb2 = (int)((K + BK - 1) / BK);
+        const int chunks2 = (total_kb2 + 2048 / BK - 1) / (2048 / BK);
+        Params q;
+        q.M = (int)M; q.N = (int)N; q.K = (int)K;
+        q.tiles_m = (int)((M + 255) / 256); q.tiles_n = (int)((N + 255) / 256);
+        q.kb_per_chunk = (total_kb2 + chunks2 - 1) / chunks2; q._pad = 0;
+        q.C = d->C; q.c_sm = d->c_sm; q.c_sn = d->c_sn; q.c_sb = d->c_sb;
+        gemm_tf32x3_2cta_kernel<<<dim3((unsigned)(2 * pair_tiles), (unsigned)batch, 1u), THREADS, Cfg2::SMEM, st>>>(pAh, pAl, pBh, pBl, q);
+        e = cudaGetLastError();
+        cudaFreeAsync(ws, st);
+        if (e != cudaSuccess) return set_error("gemm_tf32x3 (CTA pair) launch failed: %s", cudaGetErrorString(e));
+        count_launch();
+        return 0;
+    }
     CUtensorMap tAh, tAl, tBh, tBl;
     if (!make_tmap_f32(&tAh, a_hi, K, M, batch, Kp, BM * MT) || !make_tmap_f32(&tAl, a_lo, K, M, batch, Kp, BM * MT) ||
         !make_tmap_f32(&tBh, b_hi, K, N, batch, Kp, BN) || !make_tmap_f32(&tBl, b_lo, K, N, batch, Kp, BN)) {
