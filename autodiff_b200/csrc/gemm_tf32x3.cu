@@ -18,6 +18,8 @@
 //                       the cuBLAS TF32 burst rate of this pool (753; profiles/tf32_peak.json), 5.30 ms with the split passes
 //                       = 207 TFLOP/s effective (round 1, chains as separate CTAs + a reduction kernel, column-major tile
 //                       order: 6.2 ms, 11.5 GB of DRAM reads per launch against 5.9 GB now)
+//   gemm_tf32x3_2cta_kernel: the same with two CTAs of a cluster on a 256 x 256 tile (tcgen05.mma.cta_group::2, see below):
+//                       8192^3 4.23 ms kernel / 4.69 ms with the split passes = 235 TFLOP/s effective
 //   warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (one TMEM lane quadrant each)
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -306,10 +306,10 @@ def run_gpu(args):
                     "rel_err_vs_fp64": rel, "rel_err_fwd_dA_dB": rels, "bar": 1e-4,
                     "roofline": {"bound": "tensor", "achieved": round(3 * eff, 1), "peak": tf_peak, "unit": "TFLOP/s (raw tf32 MMA: 3 products per fp64 product; "
                                  "split passes and the fp64 epilogue inside the timed region)", "frac": round(3 * eff / tf_peak, 4), "peak_source": tf_src,
-                                 "traffic": 7940000000, "traffic_note": "ncu --set full, gemm_tf32x3_kernel<2> at 8192^3 (profiles/r02_ncu_summary.md): 5.93 GB read + 2.01 GB "
-                                 "written per launch vs 1.07 GB of fp32 hi/lo operands + 0.54 GB of fp64 result; tensor pipe 58 % active"},
+                                 "traffic": 8247000000, "traffic_note": "ncu --set full, gemm_tf32x3_2cta_kernel at 8192^3 (profiles/r02_ncu_summary.md): 6.43 GB read + 1.82 GB "
+                                 "written per launch vs 1.07 GB of fp32 hi/lo operands + 0.54 GB of fp64 result; kernel alone 4.23 ms = 780 TFLOP/s raw; tensor pipe 78 % active"},
                     "what": "C2a 'ij,jk->ik' 8192^2 forward + both grads with ad.precision('tf32x3'): fp64 operands split into hi+lo tf32, "
-                            "three tcgen05.mma (kind::tf32) products per tile accumulated in TMEM in chains of <= 2048, chains added in fp64 by the epilogue warps; "
+                            "three tcgen05.mma.cta_group::2 (kind::tf32) products per 256x256 CTA-pair tile accumulated in TMEM in chains of <= 2048, chains added in fp64 by the epilogue warps; "
                             "fp64 in / fp64 out; includes the split passes; error measured over the full matrices against the FP64 path"}
             del got, ref
         except Exception as ex:
