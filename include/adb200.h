@@ -67,10 +67,12 @@ ADB_API int adb_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, 
 ADB_API int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
 /* path: 0 = auto, 1 = force TMA+DMMA kernel (error if not describable), 2 = force generic kernel,
  * 3 = force TMA+DMMA with 64x64 tiles, 4 = force TMA+DMMA with 128x128 tiles, 5 = force the 256x32 tall-skinny tiles,
- * 6 = force the 128x32 tiles (few rows and few columns, long K) */
+ * 6 = force the 128x32 tiles (few rows and few columns, long K), 7 / 8 = force the stream-K kernel with 128x128 / 64x64 tiles
+ * (whole-tile CTAs for the full waves + CTAs sharing the ragged last wave along K, one launch; bitwise repeatable) */
 ADB_API int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
 /* Same contract (fp64 in, fp64 out), arithmetic as 3xTF32 on the tcgen05 tensor cores with fp32 accumulation in TMEM:
- * a ~= hi + lo, A.B ~= hi.hi + lo.hi + hi.lo  (parity bar 1e-4; measured ~1e-7). */
+ * a ~= hi + lo, A.B ~= hi.hi + lo.hi + hi.lo  (parity bar 1e-4; measured ~1e-5 at K = 8192: fp32 accumulation chains of <= 2048,
+ * chains added in fp64).  Env ADB_TF32_2CTA=0 pins the single-CTA kernel, =2 forces the CTA-pair (cta_group::2) kernel. */
 ADB_API int adb_gemm_tf32x3(const adb_gemm_desc* desc, void* stream);
 /* Contraction precision used by adb_einsum for GEMM-shaped einsums: 0 = FP64 DMMA (default), 1 = 3xTF32 tcgen05. */
 ADB_API int adb_set_precision(int precision);
