@@ -136,8 +136,6 @@ struct GemmParams {
     int blocked;                 // bit 0 / 1: the MN-contiguous A / B operand has a BLOCKED tensor map (one TMA box per tile)
     double* C;
     long long c_sm, c_sn, c_sb, c_ss;   // c_ss: stride between split-K partial results
-    int tile_offset;             // first tile (raster order) of this launch: the tail wave is a launch of its own
-    int ws_tiles;                // > 0: C is a workspace of [gridDim.z][ws_tiles] dense BM x BN tiles (tail wave, see gemm_tail_fixup)
     // implicit-GEMM convolution (CONV kernels): operand A is never materialised, tmA is an im2col-mode tensor map of the image
     int cv_wb, cv_hb;            // positions per row / rows per image of the bounding box the windows slide over
     int cv_lw, cv_lh;            // its lower corner (0 for a VALID convolution, -(k-1) for the data gradient's full convolution)
@@ -272,7 +270,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     // grouped rasterisation: 8 tile-rows share their B column panels in L2
     const int GROUP = 8;
-    const int tile = blockIdx.x + p.tile_offset;
+    const int tile = blockIdx.x;
     const int group_size = GROUP * p.tiles_n;
     const int first_m = (tile / group_size) * GROUP;
     const int gm = min(p.tiles_m - first_m, GROUP);
@@ -396,10 +394,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 
     // ===== epilogue: registers -> C (general strides; 16B vector stores when the n-stride is 1) =====
-    // (tail wave: the partial tile goes to its own dense BM x BN slot of the workspace, addressed by tile-local coordinates)
-    double* __restrict__ Cb = p.ws_tiles > 0
-        ? p.C + ((long long)blockIdx.z * p.ws_tiles + blockIdx.x) * (BM * BN) - ((long long)m0 * BN + n0)
-        : p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
+    double* __restrict__ Cb = p.C + (long long)batch * p.c_sb + (long long)blockIdx.z * p.c_ss;
     store_acc<Cfg, A_KC, B_KC>(acc, Cb, p.c_sm, p.c_sn, m0, n0, p.M, p.N, warp_m, warp_n, g, q, rmap);
 }
 
@@ -766,37 +761,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
-// ----------------------------------------------------------------------------- tail-wave fix-up
-// C tile = sum over the K-slices z (fixed order => deterministic) of the dense BM x BN partial tiles the tail launch wrote.
-__global__ void __launch_bounds__(256)
-gemm_tail_fixup(const double* __restrict__ ws, int splits, int ws_tiles, int bm, int bn, int tile_offset, int tiles_m, int tiles_n,
-                int M, int N, double* __restrict__ C, long long c_sm, long long c_sn) {
-    const int GROUP = 8;
-    const int tile = blockIdx.x + tile_offset;
-    const int group_size = GROUP * tiles_n;
-    const int first_m = (tile / group_size) * GROUP;
-    const int gm = min(tiles_m - first_m, GROUP);
-    const int tm = first_m + (tile % group_size) % gm;
-    const int tn = (tile % group_size) / gm;
-    const int m0 = tm * bm, n0 = tn * bn;
-    const long long tile_elems = (long long)bm * bn;
-    const double* base = ws + (long long)blockIdx.x * tile_elems;
-    const long long zs = (long long)ws_tiles * tile_elems;
-    for (int e = threadIdx.x * 2; e < bm * bn; e += 512) {           // bn is even: a pair never straddles a row
-        const int r = e / bn, c = e - r * bn;
-        const int row = m0 + r, col = n0 + c;
-        if (row >= M || col >= N) continue;
-        double2 acc = *reinterpret_cast<const double2*>(base + e);
-        for (int z = 1; z < splits; ++z) {
-            const double2 v = *reinterpret_cast<const double2*>(base + z * zs + e);
-            acc.x += v.x; acc.y += v.y;
-        }
-        double* cp = C + (long long)row * c_sm + (long long)col * c_sn;
-        cp[0] = acc.x;
-        if (col + 1 < N) cp[c_sn] = acc.y;
-    }
-}
-
 // ----------------------------------------------------------------------------- generic fallback
 // 64x64 tile, 256 threads, 4x4 per thread, BK=16; arbitrary element strides.
 __global__ void __launch_bounds__(256)
@@ -912,7 +876,7 @@ static bool tma_ok(const double* base, long long s_other, long long s_batch, lon
 }
 
 template <class Cfg, bool A_KC, bool B_KC, int CONV = 0>
-static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, int splits, cudaStream_t st, int ntiles = -1) {
+static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, int splits, cudaStream_t st) {
     static bool attr_set = false;
     auto kern = gemm_tma_kernel<Cfg, A_KC, B_KC, CONV>;
     constexpr int GEMM_SMEM = Cfg::SMEM;
@@ -921,7 +885,7 @@ static int launch_tma(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
         if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((unsigned)(ntiles >= 0 ? ntiles : p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch, (unsigned)splits);
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("gemm_tma launch failed: %s", cudaGetErrorString(e));
@@ -1077,12 +1041,7 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         // short K (<= 8 k-tiles): a CTA is mostly prologue + epilogue, so two 64x64 CTAs per SM that overlap each other beat
         // one 128x128 CTA (conv dX 802816x400x32: 1.38 -> 1.05 ms)
         const bool short_k = (K + BK - 1) / BK <= 8;
-        // 128x128 tiles whose last wave is at most half full and whose K is long run that wave split along K (below) instead of
-        // falling back to 64x64 tiles: 2048 x 4096 x 4097 (512 = 3 x 148 + 68 tiles) 2.03 -> 1.9x ms
-        static int tail_pref = -1;     // ADB_GEMM_TAIL=0: off (A/B measurements)
-        if (tail_pref < 0) { const char* e = getenv("ADB_GEMM_TAIL"); tail_pref = (e && e[0] == '0') ? 0 : 1; }
-        const bool big_tail = tail_pref && batch == 1 && big_tiles >= 296 && big_tiles % 148 > 0 && (big_tiles % 148) * 2 <= 148 && K >= 3072;
-        // Persistent stream-K kernel (one launch, no wave quantisation): forced by path 7 (128x128 tiles) / 8 (64x64 tiles);
+        // Stream-K kernel (one launch, no wave quantisation): forced by path 7 (128x128 tiles) / 8 (64x64 tiles);
         // chosen automatically for 128x128-tile problems whose k-loop is long enough to hide a tile's epilogue.
         static int sk_pref = -1;       // ADB_GEMM_SK=0: the one-tile-per-CTA kernels (A/B measurements)
         if (sk_pref < 0) { const char* e = getenv("ADB_GEMM_SK"); sk_pref = (e && e[0] == '0') ? 0 : 1; }
@@ -1092,7 +1051,7 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
         const bool sk_auto = sk_pref && force_path == 0 && tile_pref == 0 && !skinny && !skinny_s && !short_k && batch <= 65535 &&
                              fill_big >= 0.75 && (big_tiles >= 148 || big_tiles * ((K + BK - 1) / BK) >= 148 * 48);
         const bool sk_big = force_path == 7 || sk_auto, sk_small = force_path == 8;
-        const bool small = !sk_big && !skinny && !skinny_s && (sk_small || force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && ((waste_big > 1.05 && !big_tail) || short_k)))));
+        const bool small = !sk_big && !skinny && !skinny_s && (sk_small || force_path == 3 || (force_path != 4 && (tile_pref == 1 || (tile_pref == 0 && (waste_big > 1.05 || short_k)))));
         const int bm = skinny_s ? CfgSkinnyS::BM : skinny ? CfgSkinny::BM : small ? CfgSmall::BM : CfgBig::BM;
         const int bn = skinny_s ? CfgSkinnyS::BN : skinny ? CfgSkinny::BN : small ? CfgSmall::BN : CfgBig::BN;
         const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
@@ -1145,7 +1104,6 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
             p.kt_per_split = kt_per_split; p.blocked = blocked;
             if (splits > 1) { p.C = ws_c; p.c_sm = Np; p.c_sn = 1; p.c_sb = M * Np; p.c_ss = (long long)batch * M * Np; }
             else { p.C = d->C; p.c_sm = d->c_sm; p.c_sn = d->c_sn; p.c_sb = d->c_sb; p.c_ss = 0; }
-            p.tile_offset = 0; p.ws_tiles = 0;
             p.cv_wb = p.cv_hb = p.cv_lw = p.cv_lh = p.cv_kw = p.cv_cpt = 0;
             if (sk_big || sk_small) {
                 int rc;
@@ -1162,70 +1120,30 @@ int gemm_f64(const adb_gemm_desc* d, cudaStream_t st, int force_path) {
                 }
                 return rc;
             }
-            auto dispatch = [&](const GemmParams& pp, int sp, int ntiles) -> int {
+            auto dispatch = [&](const GemmParams& pp, int sp) -> int {
                 if (skinny_s) {
-                    if (a_kc && b_kc) return launch_tma<CfgSkinnyS, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (a_kc && !b_kc) return launch_tma<CfgSkinnyS, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (!a_kc && b_kc) return launch_tma<CfgSkinnyS, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else return launch_tma<CfgSkinnyS, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    if (a_kc && b_kc) return launch_tma<CfgSkinnyS, true, true>(ta, tb, pp, (int)batch, sp, st);
+                    else if (a_kc && !b_kc) return launch_tma<CfgSkinnyS, true, false>(ta, tb, pp, (int)batch, sp, st);
+                    else if (!a_kc && b_kc) return launch_tma<CfgSkinnyS, false, true>(ta, tb, pp, (int)batch, sp, st);
+                    else return launch_tma<CfgSkinnyS, false, false>(ta, tb, pp, (int)batch, sp, st);
                 } else if (skinny) {
-                    if (a_kc && b_kc) return launch_tma<CfgSkinny, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (a_kc && !b_kc) return launch_tma<CfgSkinny, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (!a_kc && b_kc) return launch_tma<CfgSkinny, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else return launch_tma<CfgSkinny, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    if (a_kc && b_kc) return launch_tma<CfgSkinny, true, true>(ta, tb, pp, (int)batch, sp, st);
+                    else if (a_kc && !b_kc) return launch_tma<CfgSkinny, true, false>(ta, tb, pp, (int)batch, sp, st);
+                    else if (!a_kc && b_kc) return launch_tma<CfgSkinny, false, true>(ta, tb, pp, (int)batch, sp, st);
+                    else return launch_tma<CfgSkinny, false, false>(ta, tb, pp, (int)batch, sp, st);
                 } else if (small) {
-                    if (a_kc && b_kc) return launch_tma<CfgSmall, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (a_kc && !b_kc) return launch_tma<CfgSmall, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (!a_kc && b_kc) return launch_tma<CfgSmall, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else return launch_tma<CfgSmall, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    if (a_kc && b_kc) return launch_tma<CfgSmall, true, true>(ta, tb, pp, (int)batch, sp, st);
+                    else if (a_kc && !b_kc) return launch_tma<CfgSmall, true, false>(ta, tb, pp, (int)batch, sp, st);
+                    else if (!a_kc && b_kc) return launch_tma<CfgSmall, false, true>(ta, tb, pp, (int)batch, sp, st);
+                    else return launch_tma<CfgSmall, false, false>(ta, tb, pp, (int)batch, sp, st);
                 } else {
-                    if (a_kc && b_kc) return launch_tma<CfgBig, true, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (a_kc && !b_kc) return launch_tma<CfgBig, true, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else if (!a_kc && b_kc) return launch_tma<CfgBig, false, true>(ta, tb, pp, (int)batch, sp, st, ntiles);
-                    else return launch_tma<CfgBig, false, false>(ta, tb, pp, (int)batch, sp, st, ntiles);
+                    if (a_kc && b_kc) return launch_tma<CfgBig, true, true>(ta, tb, pp, (int)batch, sp, st);
+                    else if (a_kc && !b_kc) return launch_tma<CfgBig, true, false>(ta, tb, pp, (int)batch, sp, st);
+                    else if (!a_kc && b_kc) return launch_tma<CfgBig, false, true>(ta, tb, pp, (int)batch, sp, st);
+                    else return launch_tma<CfgBig, false, false>(ta, tb, pp, (int)batch, sp, st);
                 }
             };
-            // Tail wave.  tiles = w * slots + rem: the last rem tiles would hold the machine for a whole wave while filling
-            // only rem / slots of it.  When rem <= slots / 2 the
-            // full waves run as one data-parallel launch and the tail tiles as a second launch split S = slots / rem ways
-            // along K, each slice writing a dense partial tile; gemm_tail_fixup adds the slices in order (deterministic).
-            int rc;
-            const long long tiles2d = (long long)p.tiles_m * p.tiles_n;
-            const long long full = tiles2d / slots * slots, rem = tiles2d - full;
-            int tail_s = 0;
-            // (measured, profiles/r02_gemm_tail_ab.log: the two extra launches cost ~40 us, so it pays for 128x128 tiles with a long K;
-            // 64x64 tiles lose little to their last wave - its CTAs run alone on their SMs, 1.2x faster - and got slower)
-            if (tail_pref && splits == 1 && batch == 1 && !small && !skinny && !skinny_s && (force_path == 0 || force_path == 4) &&
-                full > 0 && rem > 0 && rem * 2 <= slots && total_kt >= 64) {
-                long long sc = slots / rem;
-                if (sc > 8) sc = 8;
-                if (sc > total_kt / 16) sc = total_kt / 16;
-                if (sc >= 2) tail_s = (int)sc;
-            }
-            if (tail_s >= 2) {
-                double* ws_t = nullptr;
-                const int kts = (total_kt + tail_s - 1) / tail_s;
-                const int ns = (total_kt + kts - 1) / kts;
-                cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws_t), (size_t)ns * rem * bm * bn * sizeof(double), st);
-                if (e != cudaSuccess) return set_error("gemm: tail workspace allocation failed: %s", cudaGetErrorString(e));
-                rc = dispatch(p, 1, (int)full);
-                if (rc == 0) {
-                    GemmParams pt = p;
-                    pt.tile_offset = (int)full; pt.ws_tiles = (int)rem; pt.kt_per_split = kts;
-                    pt.C = ws_t; pt.c_sm = bn; pt.c_sn = 1; pt.c_sb = 0; pt.c_ss = 0;
-                    rc = dispatch(pt, ns, (int)rem);
-                }
-                if (rc == 0) {
-                    gemm_tail_fixup<<<(unsigned)rem, 256, 0, st>>>(ws_t, ns, (int)rem, bm, bn, (int)full, p.tiles_m, p.tiles_n, (int)M, (int)N,
-                                                                  d->C, d->c_sm, d->c_sn);
-                    e = cudaGetLastError();
-                    if (e != cudaSuccess) rc = set_error("gemm tail fix-up launch failed: %s", cudaGetErrorString(e));
-                    else count_launch();
-                }
-                cudaFreeAsync(ws_t, st);
-                return rc;
-            }
-            rc = dispatch(p, splits, -1);
+            int rc = dispatch(p, splits);
             if (rc == 0 && splits > 1) {
                 // C[b][m][n] = sum_z ws[z][b][m][n]  (deterministic order, column-mode reduction kernel)
                 ReduceSpec S;

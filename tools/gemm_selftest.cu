@@ -185,6 +185,19 @@ int main(int argc, char** argv) {
         run_case(Case{atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoll(argv[5]), atoi(argv[6]), atoi(argv[7]), 0, atoi(argv[8])}, true, 2);
         return 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "sanitize")) {       // a small set for compute-sanitizer (memcheck / racecheck): every kernel family once
+        int f = 0;
+        long long shapes[][4] = {{200, 136, 100, 1}, {257, 129, 50, 3}, {384, 256, 1024, 1}, {640, 640, 1040, 1}, {1281, 1100, 600, 1}, {300, 200, 2100, 2}};
+        for (auto& s : shapes) for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) {
+            for (int path : {0, 3, 4, 7, 8}) f += run_case(Case{s[0], s[1], s[2], s[3], a, b, 0, path}, false, 0);
+            f += run_tf32(s[0], s[1], s[2], s[3], a, b, false);
+            f += run_tf32(s[0], s[1], s[2], s[3], a, b, false, true);
+        }
+        f += run_case(Case{1000, 32, 75, 1, 1, 0, 0, 5}, false, 0);
+        f += run_case(Case{75, 16, 30000, 1, 0, 0, 0, 6}, false, 0);
+        printf("sanitize set: %d failing cases\n", f);
+        return f ? 1 : 0;
+    }
     if (argc > 2 && !strcmp(argv[1], "tf32one")) {         // one timed 3xTF32 case (for ncu): tf32one N [b_kc]
         const long long n = atoll(argv[2]);
         run_tf32(n, n, n, 1, 1, argc > 3 ? atoi(argv[3]) : 0, true, true);
@@ -196,6 +209,7 @@ int main(int argc, char** argv) {
                                  {256, 256, 4100, 1}, {300, 200, 8200, 2}, {1024, 1536, 4097, 1}, {4097, 1536, 1024, 1}, {2560, 2048, 6200, 1}};   // K > 2048: several fp32 chains
         for (auto& s : shapes) for (int a = 1; a >= 0; --a) for (int b = 1; b >= 0; --b) fails += run_tf32(s[0], s[1], s[2], s[3], a, b, false);
         printf("tf32x3 correctness: %d failing cases\n", fails);
+        if (argc > 2 && !strcmp(argv[2], "check")) return fails ? 1 : 0;
         for (long long n : {2048ll, 4096ll, 8192ll}) run_tf32(n, n, n, 1, 1, 0, true, true);
         run_tf32(8192, 8192, 8192, 1, 1, 1, true, true);
         run_tf32(8192, 8192, 8192, 1, 0, 0, true, true);
@@ -258,6 +272,7 @@ int main(int argc, char** argv) {
             for (auto& s : shapes) for (int path : {7, 8}) f += run_case(Case{s[0], s[1], s[2], s[3], a, b, 0, path}, false, 0);
         }
         printf("stream-K correctness: %d failing cases\n", f);
+        if (argc > 2 && !strcmp(argv[2], "check")) return f ? 1 : 0;      // correctness only (compute-sanitizer runs)
         // run-to-run bitwise repeatability is checked by tests/test_gpu_parity.py; here: speed against the one-tile-per-CTA kernels
         long long shp[][5] = {{1024, 4096, 4097, 1, 1}, {1024, 4096, 4096, 1, 3}, {4096, 4096, 1024, 1, 0}, {2048, 4096, 4097, 1, 1}, {4097, 4096, 2048, 1, 0},
                               {512, 1024, 1024, 1, 1}, {512, 1024, 1024, 1, 3}, {1024, 1024, 512, 1, 0}, {512, 71, 1024, 1, 1}, {71, 1024, 512, 1, 0},
@@ -277,7 +292,7 @@ int main(int argc, char** argv) {
         for (auto& s : shp) for (int path : {3, 4, 7}) run_case(Case{s[0], s[1], s[2], s[3], (int)(s[4] & 1), (int)((s[4] >> 1) & 1), 0, path}, true, 5);
         return 0;
     }
-    if (argc > 1 && !strcmp(argv[1], "tail")) {            // shapes whose last wave is split along K (ADB_GEMM_TAIL=0 turns it off)
+    if (argc > 1 && !strcmp(argv[1], "tail")) {            // shapes with a ragged last wave (stream-K; ADB_GEMM_SK=0: one tile per CTA)
         run_case(Case{1024, 4096, 4097, 1, 1, 0, 0, 0}, true, 5);    // C3 forward on a 1024-row shard
         run_case(Case{1024, 4096, 4096, 1, 1, 1, 0, 0}, true, 5);    // its dX (ragged column cut off by the planner)
         run_case(Case{4096, 4096, 1024, 1, 0, 0, 0, 0}, true, 5);    // its dW (6.9 waves: no tail)
