@@ -40,7 +40,10 @@ def _hammer(ad, bufs, stream):
 
 
 @pytest.mark.parametrize("path,m,n,k,layout", [(3, 2048, 4096, 4096, 0), (3, 1024, 4096, 4096, 0), (3, 512, 1024, 1024, 0),
-                                               (3, 2048, 4096, 2048, 1), (4, 2048, 4096, 4096, 0), (0, 1000, 4097, 520, 0)])
+                                               (3, 2048, 4096, 2048, 1), (4, 2048, 4096, 4096, 0), (0, 1000, 4097, 520, 0),
+                                               # the stream-K kernel (whole-tile CTAs + K-sharing CTAs with the last-arriver fix-up):
+                                               (7, 1024, 4096, 4096, 0), (7, 2048, 4096, 2048, 1), (7, 1024, 1024, 4096, 0), (8, 512, 1024, 1024, 0),
+                                               (0, 1024, 4096, 4096, 0)])
 def test_gemm_bitwise_under_concurrent_hbm_traffic(ad, path, m, n, k, layout):
     import torch
     from autodiff_b200 import _lib
