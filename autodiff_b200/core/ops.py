@@ -484,6 +484,10 @@ class SoftmaxCEWithLogits(Node):
         super().__init__([labels, logits], name=name)
         self.labels, self.logits = self.children
         self.shape = tuple(self.logits.shape[:-1])
+        if self.labels.shape is None or len(self.labels.shape) != 2 or len(self.logits.shape) != 2:
+            # the N-D path checks the labels on the HOST (axis-1 sums read back synchronously) and ignores the kernel's own
+            # last-axis flag: a launch tape would replay neither decision, so a graph that holds such a node is never taped
+            self._never_tape = True
 
     def _eval_device(self):
         lab, z = dev(self.labels), dev(self.logits)

@@ -51,6 +51,13 @@ MAX_TAPES = 64
 GRAPH = os.environ.get("ADB_TAPE_GRAPH", "1") != "0"
 GRAPH_AFTER_REPLAYS = int(os.environ.get("ADB_TAPE_GRAPH_AFTER", "1"))   # call-by-call replays before a tape is captured (0 with
 GRAPH_MIN_CALLS = int(os.environ.get("ADB_TAPE_GRAPH_MIN_CALLS", "4"))   # ADB_TAPE_SELFCHECK=1: every graph of the test-suite)
+GRAPH_STREAMS = max(1, int(os.environ.get("ADB_TAPE_GRAPH_STREAMS", "4")))   # capture streams: independent calls of a tape become parallel
+                                                                             # branches of the CUDA graph (1 = one linear chain)
+# Which arguments of a recorded entry point are WRITTEN (include/adb200.h); every other tensor / pointer argument is read.  A tape
+# that holds a call missing here is captured as one chain.
+_OUT_ARGS = {"adb_ewise": (5,), "adb_einsum": (3,), "adb_reduce_sum": (1,), "adb_sum_squares": (1,), "adb_norm2": (1,),
+             "adb_softmax_ce": (2,), "adb_im2col": (3,), "adb_col2im": (3,), "adb_conv_gemm": (5,), "adb_memcpy_d2d": (0,),
+             "adb_memset_async": (0,)}
 GRAPH_MAX_STAGE_BYTES = 64 << 20       # leaves are copied next to the arena on every replay: only worth it when they are small
 # All graph buffers together (they outlive the step): 64 GB of the 180 GB.  The second-order char-rnn's arena is 26 GB; while
 # its Python graph build dominated the evaluation its graph measured a wash (profiles/r01_graph_ab.log), but with deferred
@@ -63,6 +70,7 @@ _tapes = {}              # signature -> Tape | False (not tapeable)
 _recorder = None         # active Recorder (set while a recording evaluation runs)
 stats = {"replays": 0, "records": 0, "rejected": 0, "graphs": 0, "graph_launches": 0, "graph_rejected": 0, "graph_busy": 0, "graph_bytes": 0}
 _cap_stream = None       # side stream the graphs are captured on (the legacy default stream cannot be captured)
+_cap_side = []           # further capture streams: parallel branches of a graph (GRAPH_STREAMS)
 
 # node classes whose device evaluation is a pure function of (class, these attributes, children): filled by register()
 _ATTRS = {}
@@ -156,8 +164,9 @@ def scan(tops, scalar_of, has_value, is_device_node):
         if not kind[1]:
             return None
         nd = n.__dict__
-        if "_eval" in nd or "_eval_device" in nd:
-            return None                          # an instance-level override: not a pure function of (class, attributes)
+        if "_eval" in nd or "_eval_device" in nd or "_never_tape" in nd:
+            return None                          # an instance-level override / a node that decides on the host: not a pure
+                                                 # function of (class, attributes) that a replay could reproduce
         attrs = kind[2]
         children = n.children
         if attrs:
@@ -208,7 +217,7 @@ class Recorder:
 
 
 class _Call:
-    __slots__ = ("fn", "args", "patches", "void_patches", "flag_arg")
+    __slots__ = ("fn", "args", "patches", "void_patches", "flag_arg", "reads", "writes")   # reads / writes: buffer indices, None = unknown
 
 
 class Tape:
@@ -296,6 +305,8 @@ def build_tape(rec, order, leaves, n_tops):
     for name, fn, args in rec.calls:
         c = _Call()
         c.fn, c.args, c.patches, c.void_patches, c.flag_arg = fn, list(args), [], [], -1
+        outs = _OUT_ARGS.get(name)
+        c.reads, c.writes = (set(), set()) if outs is not None else (None, None)
         for ai, a in enumerate(args):
             for ts in _tensor_structs(a):
                 if not ts.ptr:
@@ -305,6 +316,8 @@ def build_tape(rec, order, leaves, n_tops):
                     return None
                 if r[0] >= 0:
                     c.patches.append((ts, r[0], r[1]))
+                    if outs is not None:
+                        (c.writes if ai in outs else c.reads).add(r[0])
             if isinstance(a, C.c_void_p) and a.value:
                 if name == "adb_softmax_ce" and ai == 3:
                     c.flag_arg = ai              # a fresh zeroed flag per replay
@@ -316,6 +329,8 @@ def build_tape(rec, order, leaves, n_tops):
                         return None
                     if r[0] >= 0:
                         c.void_patches.append((ai, r[0], r[1]))
+                        if outs is not None:
+                            (c.writes if ai in outs else c.reads).add(r[0])
         tape.calls.append(c)
     # --- where every materialised node's value lives
     values = []
@@ -346,6 +361,50 @@ def build_tape(rec, order, leaves, n_tops):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA-graph replay
+def plan_streams(calls, k):
+    """List scheduling of a tape's calls onto k capture streams from their buffer read / write sets (RAW, WAW and WAR on whole
+    buffers: two calls that touch different views of one buffer are ordered - conservative, never wrong).  Returns (stream of each
+    call, calls on OTHER streams each call waits for, set of calls that must record an event), or None when some call's sets are
+    unknown.  A call goes onto the stream whose tail is one of its predecessors (no event needed), else onto the stream idle longest."""
+    if k <= 1 or any(c.reads is None for c in calls):
+        return None
+    last_writer, readers = {}, {}
+    tail = [-1] * k
+    assign, waits = [], []
+    for i, c in enumerate(calls):
+        deps = set()
+        for b in c.reads:
+            w = last_writer.get(b)
+            if w is not None:
+                deps.add(w)
+        for b in c.writes:
+            w = last_writer.get(b)
+            if w is not None:
+                deps.add(w)
+            deps.update(readers.get(b, ()))
+        st = -1
+        for d in sorted(deps, reverse=True):
+            if tail[assign[d]] == d:
+                st = assign[d]
+                break
+        if st < 0:
+            st = min(range(k), key=lambda j: tail[j])
+        latest = {}
+        for d in deps:
+            if assign[d] != st and d > latest.get(assign[d], -1):
+                latest[assign[d]] = d              # stream order implies the earlier calls of that stream
+        waits.append(sorted(latest.values()))
+        assign.append(st)
+        tail[st] = i
+        for b in c.writes:
+            last_writer[b] = i
+            readers[b] = []
+        for b in c.reads:
+            if b not in c.writes:
+                readers.setdefault(b, []).append(i)
+    return assign, waits, {d for w in waits for d in w}
+
+
 def _capture(tape):
     """Issues the tape's calls against a private buffer: once eagerly on the capture stream (sizes every grow-only
     workspace of the library for that stream, so nothing allocates while recording), once in capture mode."""
@@ -375,22 +434,54 @@ def _capture(tape):
     bases = [b0 + 8 * o for o in g.stage_off] + [b0 + 8 * (total + o) for o in tape.slot_off]
     sp = C.c_void_p(_cap_stream.cuda_stream)
     check = _lib.check
+    # independent calls go to different capture streams and become parallel branches of the graph (fork / join through events)
+    plan = plan_streams(tape.calls, GRAPH_STREAMS) if len(tape.calls) >= 8 else None
+    if plan is not None:
+        global _cap_side
+        while len(_cap_side) < GRAPH_STREAMS - 1:
+            _cap_side.append(t.cuda.Stream())
+        streams = [_cap_stream] + _cap_side[:GRAPH_STREAMS - 1]
+        sps = [C.c_void_p(x.cuda_stream) for x in streams]
+        assign, waits, need_event = plan
+        if len(set(assign)) == 1:
+            plan = None                           # a pure chain
 
     def issue():
         fi = 0
-        for c in tape.calls:
+        events = {}
+        if plan is not None:                      # fork: the side streams join the capture behind everything queued so far
+            ev = t.cuda.Event()
+            ev.record(_cap_stream)
+            for x in streams[1:]:
+                x.wait_event(ev)
+        for i, c in enumerate(tape.calls):
             for ts, j, off in c.patches:
                 ts.ptr = bases[j] + off
             args = list(c.args)
             for ai, j, off in c.void_patches:
                 args[ai] = C.c_void_p(bases[j] + off)
-            args[-1] = sp                         # every compute entry point takes the stream last
+            if plan is not None:
+                k = assign[i]
+                for d in waits[i]:
+                    streams[k].wait_event(events[d])
+                cs = sps[k]
+            else:
+                cs = sp
+            args[-1] = cs                         # every compute entry point takes the stream last
             if c.flag_arg >= 0:
                 fp = C.c_void_p(f0 + 4 * fi)
                 fi += 1
-                check(L.adb_memset_async(fp, 0, 4, sp))      # part of the graph: each launch starts from a clean flag
+                check(L.adb_memset_async(fp, 0, 4, cs))      # part of the graph: each launch starts from a clean flag
                 args[c.flag_arg] = fp
             check(c.fn(*args))
+            if plan is not None and i in need_event:
+                ev = events[i] = t.cuda.Event()
+                ev.record(streams[assign[i]])
+        if plan is not None:                      # join: the origin stream ends behind every branch
+            for x in streams[1:]:
+                ev = t.cuda.Event()
+                ev.record(x)
+                _cap_stream.wait_event(ev)
     try:
         issue()
         check(L.adb_sync(sp))
@@ -404,13 +495,15 @@ def _capture(tape):
                 L.adb_graph_destroy(ex)
             raise
         check(L.adb_graph_end(sp, C.byref(ex)))
-    except (_lib.BackendError, ValueError):
+    except (_lib.BackendError, ValueError, RuntimeError):
         stats["graph_rejected"] += 1
         return False
     g.exec = ex
     g.last_stream = None
     g.refs = sys.getrefcount(g.buf)
     stats["graphs"] += 1
+    if plan is not None:
+        stats["graph_branches"] = stats.get("graph_branches", 0) + len(set(assign))
     return g
 
 

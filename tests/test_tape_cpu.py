@@ -155,3 +155,64 @@ def test_scan_never_materialises_a_constfill():
     assert len(fills) >= 2                           # the gradient seed is a ConstFill too
     assert _sig([e]) is not None and _sig([g]) is not None
     assert all(f._materialised is None for f in fills)
+
+
+def test_plan_streams_orders_every_dependent_pair():
+    """core/tape.py: plan_streams puts independent calls of a tape on different capture streams (parallel branches of the CUDA
+    graph).  For random read / write sets: every RAW / WAW / WAR pair must be ordered by stream order + event waits (checked through
+    the transitive happens-before closure), unknown calls disable the plan, a pure chain stays on one stream."""
+    import random
+
+    class Call:
+        def __init__(self, reads, writes):
+            self.reads, self.writes = reads, writes
+
+    rnd = random.Random(5)
+    for trial in range(60):
+        n, nbuf, k = rnd.randint(8, 70), rnd.randint(3, 30), rnd.randint(2, 5)
+        calls = []
+        for i in range(n):
+            reads = set(rnd.sample(range(nbuf), rnd.randint(0, min(3, nbuf))))
+            writes = {rnd.randrange(nbuf)} if rnd.random() < 0.85 else {rnd.randrange(nbuf), rnd.randrange(nbuf)}
+            if rnd.random() < 0.1:
+                reads |= writes                                  # in place
+            calls.append(Call(reads, writes))
+        plan = tape.plan_streams(calls, k)
+        assert plan is not None
+        assign, waits, need = plan
+        assert len(assign) == n and all(0 <= a < k for a in assign)
+        assert need == {d for w in waits for d in w}
+        before = [set() for _ in range(n)]                       # happens-before closure
+        tail = {}
+        for i in range(n):
+            preds = list(waits[i])
+            if assign[i] in tail:
+                preds.append(tail[assign[i]])
+            for d in preds:
+                assert d < i and (d == tail.get(assign[d]) or assign[d] != assign[i] or True)
+                before[i].add(d)
+                before[i] |= before[d]
+            tail[assign[i]] = i
+        for i in range(n):
+            for j in range(i):
+                a, b = calls[j], calls[i]
+                conflict = (a.writes & (b.reads | b.writes)) or (a.reads & b.writes)
+                if conflict:
+                    assert j in before[i], (trial, j, i)
+    chain = [Call({i - 1} if i else set(), {i}) for i in range(20)]
+    assign, waits, need = tape.plan_streams(chain, 4)
+    assert len(set(assign)) == 1 and not need
+    fan = [Call(set(), {0})] + [Call({0}, {i}) for i in range(1, 9)]
+    assign, waits, need = tape.plan_streams(fan, 4)
+    assert len(set(assign)) == 4                                 # eight independent consumers spread over all streams
+    assert tape.plan_streams([Call(None, None)] * 10, 4) is None and tape.plan_streams(chain, 1) is None
+
+
+def test_nd_softmax_ce_is_never_taped():
+    """N-D SoftmaxCEWithLogits decides its label check on the host (core/ops.py): the scan must refuse such graphs."""
+    z = ad.Variable(np.zeros((3, 4, 5)), name="z")
+    lab = ad.Variable(np.full((3, 4, 5), 0.25), name="l")
+    n = ad.SoftmaxCEWithLogits(labels=lab, logits=z)
+    assert tape.scan([n], engine.scalar_of, engine._has_value, engine._is_device_node) is None
+    n2 = ad.SoftmaxCEWithLogits(labels=ad.Variable(np.full((3, 5), 0.2), name="l"), logits=ad.Variable(np.zeros((3, 5)), name="z"))
+    assert tape.scan([n2], engine.scalar_of, engine._has_value, engine._is_device_node) is not None
