@@ -8,6 +8,9 @@
 // direct register epilogue.  Lane 0 of warp 0 doubles as the TMA producer (4 k-tiles ahead).  tcgen05 has no f64 kind
 // (ptxas rejects .kind::f64), so on B200 the FP64 tensor path IS the warp-level DMMA; measured issue
 // peak 37.0 TFLOP/s (profiles/r01_probe_fp64_issue_rates.log).
+// Stream-K (gemm_sk_kernel): the same loop for the full waves of tiles, plus CTAs that share the ragged last wave along K with a
+// last-arriver fix-up in k order - one launch, no wave quantisation, bitwise repeatable (profiles/r02_gemm_streamk.md).
+// Implicit-GEMM convolution (CONV = 1, conv_wgrad_kernel): the A operand is an NHWC image read through im2col-mode tensor maps.
 //
 // Shared-memory fragment addressing is conflict-free under the TMA 128B swizzle for both operand
 // layouts (see DESIGN.md "GEMM fragment maps"):
