@@ -408,7 +408,7 @@ def plan_streams(calls, k):
 def _capture(tape):
     """Issues the tape's calls against a private buffer: once eagerly on the capture stream (sizes every grow-only
     workspace of the library for that stream, so nothing allocates while recording), once in capture mode."""
-    global _cap_stream
+    global _cap_stream, _cap_side
     t = torch()
     L = _lib.lib()
     g = _Graph()
@@ -437,7 +437,6 @@ def _capture(tape):
     # independent calls go to different capture streams and become parallel branches of the graph (fork / join through events)
     plan = plan_streams(tape.calls, GRAPH_STREAMS) if len(tape.calls) >= 8 else None
     if plan is not None:
-        global _cap_side
         while len(_cap_side) < GRAPH_STREAMS - 1:
             _cap_side.append(t.cuda.Stream())
         streams = [_cap_stream] + _cap_side[:GRAPH_STREAMS - 1]
