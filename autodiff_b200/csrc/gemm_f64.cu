@@ -906,21 +906,10 @@ static int sm_count() {
     return sms;
 }
 
-// Stream-K launch: fills in the schedule (see gemm_sk_kernel), allocates the partial-tile workspace when some tile
-// is split, launches ONE kernel.  min_units: a CTA's share of the stream-K region is never shorter than this many k-tiles.
-template <class Cfg, bool A_KC, bool B_KC>
-static int launch_sk(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int batch, cudaStream_t st) {
-    static bool attr_set = false;
-    auto kern = gemm_sk_kernel<Cfg, A_KC, B_KC>;
-    constexpr int SMEM = Cfg::SMEM;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    static int min_units = -1;         // ADB_GEMM_SK_MIN_UNITS (experiments)
-    if (min_units < 0) { const char* e = getenv("ADB_GEMM_SK_MIN_UNITS"); min_units = e ? atoi(e) : 8; if (min_units < 1) min_units = 1; }
-    const long long slots = (long long)sm_count() * Cfg::MINB;
+// The stream-K schedule of a problem whose tile grid (tiles_m, tiles_n) is already set: full waves taken whole, the k-tiles of the
+// remaining tiles dealt out to <= `slots` CTAs in shares of >= min_units (see gemm_sk_kernel).  Pure host arithmetic
+// (adb_gemm_sk_plan exposes it to the CPU tests).
+static int sk_schedule(GemmParams& p, int batch, long long slots, int min_units) {
     p.total_kt = (p.K + BK - 1) / BK;
     p.batch = batch;
     p.tiles_total = (long long)p.tiles_m * p.tiles_n * batch;
@@ -936,6 +925,26 @@ static int launch_sk(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p,
         if (c > slots) c = slots;
         p.sk_ctas = (int)c;
     }
+    return 0;
+}
+
+// Stream-K launch: fills in the schedule (see gemm_sk_kernel), allocates the partial-tile workspace when some tile
+// is split, launches ONE kernel.  min_units: a CTA's share of the stream-K region is never shorter than this many k-tiles.
+template <class Cfg, bool A_KC, bool B_KC>
+static int launch_sk(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int batch, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = gemm_sk_kernel<Cfg, A_KC, B_KC>;
+    constexpr int SMEM = Cfg::SMEM;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    static int min_units = -1;         // ADB_GEMM_SK_MIN_UNITS (experiments)
+    if (min_units < 0) { const char* e = getenv("ADB_GEMM_SK_MIN_UNITS"); min_units = e ? atoi(e) : 8; if (min_units < 1) min_units = 1; }
+    const long long slots = (long long)sm_count() * Cfg::MINB;
+    if (int rc = sk_schedule(p, batch, slots, min_units)) return rc;
+    const long long rem = p.tiles_total - p.dp_tiles;
     const long long grid = p.dp_tiles + p.sk_ctas;
     void* ws = nullptr;
     if (rem > 0 && p.sk_ctas != rem) {
@@ -1409,6 +1418,17 @@ int conv_gemm_wgrad(const adb_tensor* img, int kh, int kw, const double* D, long
 
 }  // namespace adb
 
+extern "C" int adb_gemm_sk_plan(long long M, long long N, long long K, long long batch, int bm, int bn, long long slots, int min_units, long long* out) {
+    if (M <= 0 || N <= 0 || K <= 0 || batch <= 0 || bm <= 0 || bn <= 0 || slots <= 0 || min_units <= 0 || !out) return adb::set_error("adb_gemm_sk_plan: bad argument");
+    if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff || batch > 0x7fffffff) return adb::set_error("adb_gemm_sk_plan: extent too large");
+    adb::GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.tiles_m = (int)((M + bm - 1) / bm); p.tiles_n = (int)((N + bn - 1) / bn);
+    if (int rc = adb::sk_schedule(p, (int)batch, slots, min_units)) return rc;
+    out[0] = p.total_kt; out[1] = p.tiles_total; out[2] = p.dp_tiles; out[3] = p.sk_units; out[4] = p.sk_ctas; out[5] = p.dp_tiles + p.sk_ctas;
+    return 0;
+}
 extern "C" int adb_gemm_f64(const adb_gemm_desc* desc, void* stream) {
     return adb::gemm_f64(desc, reinterpret_cast<cudaStream_t>(stream), 0);
 }

@@ -70,6 +70,9 @@ ADB_API int adb_gemm_f64(const adb_gemm_desc* desc, void* stream);
  * 6 = force the 128x32 tiles (few rows and few columns, long K), 7 / 8 = force the stream-K kernel with 128x128 / 64x64 tiles
  * (whole-tile CTAs for the full waves + CTAs sharing the ragged last wave along K, one launch; bitwise repeatable) */
 ADB_API int adb_gemm_f64_path(const adb_gemm_desc* desc, void* stream, int path);
+/* The stream-K schedule the GEMM would use for tiles of bm x bn on `slots` CTA slots (no GPU needed; CPU tests of the schedule):
+ * out[0..5] = k-tiles per tile, tiles, tiles taken whole (full waves), k-tile units of the shared region, CTAs sharing it, grid size. */
+ADB_API int adb_gemm_sk_plan(long long M, long long N, long long K, long long batch, int bm, int bn, long long slots, int min_units, long long* out);
 /* Same contract (fp64 in, fp64 out), arithmetic as 3xTF32 on the tcgen05 tensor cores with fp32 accumulation in TMEM:
  * a ~= hi + lo, A.B ~= hi.hi + lo.hi + hi.lo  (parity bar 1e-4; measured ~1e-5 at K = 8192: fp32 accumulation chains of <= 2048,
  * chains added in fp64).  Env ADB_TF32_2CTA=0 pins the single-CTA kernel, =2 forces the CTA-pair (cta_group::2) kernel. */
