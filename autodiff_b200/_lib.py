@@ -52,6 +52,7 @@ PROTOTYPES = {
     "adb_memcpy2d_d2h": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "adb_gemm_f64": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "adb_gemm_f64_path": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p, C.c_int]),
+    "adb_gemm_sk_plan": (C.c_int, [C.c_longlong] * 4 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_longlong)]),
     "adb_gemm_tf32x3": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "adb_set_precision": (C.c_int, [C.c_int]),
     "adb_get_precision": (C.c_int, []),

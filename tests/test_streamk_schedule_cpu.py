@@ -16,10 +16,7 @@ from autodiff_b200 import _lib
 
 def plan(M, N, K, batch, bm, bn, slots, min_units):
     out = (C.c_longlong * 6)()
-    L = _lib.lib()
-    L.adb_gemm_sk_plan.argtypes = [C.c_longlong] * 4 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_longlong)]
-    L.adb_gemm_sk_plan.restype = C.c_int
-    _lib.check(L.adb_gemm_sk_plan(M, N, K, batch, bm, bn, slots, min_units, out))
+    _lib.check(_lib.lib().adb_gemm_sk_plan(M, N, K, batch, bm, bn, slots, min_units, out))
     return dict(total_kt=out[0], tiles=out[1], dp_tiles=out[2], sk_units=out[3], sk_ctas=out[4], grid=out[5])
 
 
