@@ -260,3 +260,18 @@ def test_every_translation_unit_is_built():
     assert len(objs) == len(set(objs))
     script = open(os.path.join(os.path.dirname(os.path.dirname(build.__file__)), "tools", "build_selftest.sh")).read()
     assert "autodiff_b200/build/*.o" in script
+
+
+def test_c3_parity_verdict_on_measured_records():
+    """training_bench.c3_parity_ok on the records the bench produced (profiles/r02_bench_line_n2_v3 / _n8_v2) and on the round-1
+    failure (loss off by 4.6e-6 at N = 4, runs not repeatable): bench.py's exit code hangs on this function."""
+    from autodiff_b200.training_bench import c3_parity_ok
+    n2 = [0.0, 0.0, 2.13e-16, 2.14e-16, 1.07e-15, 2.37e-15, 1.26e-12, 3.16e-14, 2.86e-14]
+    n8 = [0.0, 0.0, 2.13e-16, 0.0, 2.14e-15, 4.53e-15, 2.21e-12, 5.47e-14, 4.97e-14]
+    assert c3_parity_ok(n2, 1.14e-13, True, 2.04e-9, 3.89e-8, 2.42e-11)
+    assert c3_parity_ok(n8, 2.60e-13, True, 3.58e-9, 3.89e-8, 2.42e-11)
+    assert not c3_parity_ok(n8, 2.60e-13, False, 3.58e-9, 3.89e-8, 2.42e-11)               # not repeatable
+    assert not c3_parity_ok([0.0] * 8 + [4.6e-6], 1e-13, True, 1e-5, 3.89e-8, 2.42e-11)      # the round-1 race
+    assert not c3_parity_ok(n8, 3e-12, True, 3.58e-9, 3.89e-8, 2.42e-11)                     # gradients at identical inputs off the bar
+    assert not c3_parity_ok([2e-12] + n8[1:], 1e-13, True, 3.58e-9, 3.89e-8, 2.42e-11)       # loss at identical weights off the bar
+    assert not c3_parity_ok(n8, 1e-13, True, 1e-7, 3.89e-8, 2.42e-11)                        # weights beyond the 1-ulp noise floor
