@@ -30,6 +30,7 @@ struct ReduceSpec {           // dims innermost-first, already collapsed (see re
 int reduce_run(const ReduceSpec& S, cudaStream_t st);
 int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st);
 int softmax_ce_ring_try(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st);
+int sce_exp_tab();         // 1 = the table-based exp in the log-sum-exp kernels (default), 0 = the degree-13 Taylor variant
 int softmax_ce_ring_narrow_try(const adb_tensor* labels, const adb_tensor* logits, const adb_tensor* out, int* flag, cudaStream_t st);
 }  // namespace adb
 

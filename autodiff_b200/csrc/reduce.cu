@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const double* __restric
 template <int K, int NT>
 __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
                                                              long long z_sr, double* __restrict__ out, long long o_s, long long rows,
-                                                             unsigned cols, int* __restrict__ flag) {
+                                                             unsigned cols, int* __restrict__ flag, int exp_tab) {
     constexpr int NW = NT / 32;
     __shared__ double sm[4][NW];
     const long long r = blockIdx.x;
@@ -852,10 +852,20 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const unsigned c = (k * (unsigned)NT + threadIdx.x) * 4u + e;
-            se += exp_nonpos(zq[k].v[e] - mm);         // straight-line (no branch per element): the 4K evaluations interleave;
             dot += c < cols ? lq[k].v[e] * zq[k].v[e] : 0.0;   // padding is -inf -> exp = 0
             lsum += lq[k].v[e];
         }
+    }
+    if (exp_tab) {                                             // (uniform branch: one of two straight-line copies; the 4K evaluations interleave)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) se += exp_nonpos_tab(zq[k].v[e] - mm);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) se += exp_nonpos(zq[k].v[e] - mm);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -902,7 +912,7 @@ __global__ void __launch_bounds__(NT) softmax_ce_wide_kernel(const double* __res
 template <int K>
 __global__ void __launch_bounds__(256) softmax_ce_warp_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits,
                                                               long long z_sr, double* __restrict__ out, long long o_s, long long rows,
-                                                              unsigned cols, int* __restrict__ flag) {
+                                                              unsigned cols, int* __restrict__ flag, int exp_tab) {
     const unsigned lane = threadIdx.x & 31;
     const long long wstep = (long long)gridDim.x * 8;
     for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstep) {
@@ -938,10 +948,20 @@ __global__ void __launch_bounds__(256) softmax_ce_warp_kernel(const double* __re
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const unsigned c = (k * 32u + lane) * 4u + e;
-                se += exp_nonpos(zq[k].v[e] - mm);
                 dot += c < cols ? lq[k].v[e] * zq[k].v[e] : 0.0;
                 lsum += lq[k].v[e];
             }
+        }
+        if (exp_tab) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) se += exp_nonpos_tab(zq[k].v[e] - mm);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) se += exp_nonpos(zq[k].v[e] - mm);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -961,6 +981,12 @@ __global__ void __launch_bounds__(256) softmax_ce_warp_kernel(const double* __re
 // (A TMA-staged persistent variant - one 512-thread CTA per SM, rows prefetched into a shared-memory ring with 1-D bulk
 // copies - was measured at 0.47 of the HBM roof against 0.66 for the kernel above: with 64 KB per row only one CTA fits
 // per SM, and the per-row dependent chain (max -> exp -> sum -> log) then has no second CTA to overlap with.)
+
+int sce_exp_tab() {                               // ADB_SCE_EXP=taylor: the degree-13 exp_nonpos instead of the table variant (A/B measurements)
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("ADB_SCE_EXP"); mode = (e && !strcmp(e, "taylor")) ? 0 : 1; }
+    return mode;
+}
 
 static bool sce_ring_enabled() {                 // ADB_SCE_RING=0 pins the register-resident kernels (A/B measurements, tests)
     const char* e = getenv("ADB_SCE_RING");
@@ -989,7 +1015,7 @@ int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb
         long long blocks = (rows + 7) / 8;
         if (blocks > 148 * 32) blocks = 148 * 32;
 #define ADB_SCEW(KK) softmax_ce_warp_kernel<KK><<<(unsigned)blocks, 256, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
-                                                                                   out->stride[0], rows, (unsigned)cols, flag)
+                                                                                   out->stride[0], rows, (unsigned)cols, flag, sce_exp_tab())
         if (cols <= 128) ADB_SCEW(1);
         else if (cols <= 256) ADB_SCEW(2);
         else ADB_SCEW(4);
@@ -997,7 +1023,7 @@ int softmax_ce_run(const adb_tensor* labels, const adb_tensor* logits, const adb
     } else if (quad_ok && cols >= 512 && cols <= 8192 && rows < (1LL << 31)) {
         const unsigned g = (unsigned)rows;
 #define ADB_SCE(KK, NTT) softmax_ce_wide_kernel<KK, NTT><<<g, NTT, 0, st>>>(labels->ptr, labels->stride[0], logits->ptr, logits->stride[0], out->ptr, \
-                                                                            out->stride[0], rows, (unsigned)cols, flag)
+                                                                            out->stride[0], rows, (unsigned)cols, flag, sce_exp_tab())
         if (cols <= 1024) ADB_SCE(1, 256);
         else if (cols <= 2048) ADB_SCE(2, 256);
         else if (cols <= 4096) ADB_SCE(2, 512);

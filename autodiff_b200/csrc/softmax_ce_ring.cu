@@ -67,7 +67,7 @@ template <int P, int GROUPS, int SPG, int GT, int HALVES>
 __global__ void __launch_bounds__(GROUPS * GT, 1)
 softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits, long long z_sr,
                        double* __restrict__ out, long long o_s, long long rows, unsigned cols, unsigned half_bytes,
-                       int* __restrict__ flag) {
+                       int* __restrict__ flag, int exp_tab) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) unsigned long long bars[GROUPS * SPG];
     constexpr int NW = GT / 32;
@@ -142,8 +142,13 @@ softmax_ce_ring_kernel(const double* __restrict__ labels, long long l_sr, const 
         const double mm = m == -INFINITY ? 0.0 : m;
         if (HALVES > 1) sew *= (mw == -INFINITY) ? 0.0 : exp_nonpos(mw - m);   // earlier halves, rescaled to the new warp max
         double se = 0.0;
+        if (exp_tab) {                                 // (uniform branch; straight-line: the 2P evaluations interleave; padding: exp(-inf) = 0)
 #pragma unroll
-        for (int e = 0; e < 2 * P; ++e) se += exp_nonpos(z[e] - mm);  // straight-line: the 2P evaluations interleave; padding: exp(-inf) = 0
+            for (int e = 0; e < 2 * P; ++e) se += exp_nonpos_tab(z[e] - mm);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 2 * P; ++e) se += exp_nonpos(z[e] - mm);
+        }
         sew += se;
         mw = m;
         if (h != HALVES - 1) continue;                 // the row's second half follows in the next unit
@@ -193,7 +198,7 @@ cudaError_t launch_ring(const adb_tensor* labels, const adb_tensor* logits, cons
     }
     softmax_ce_ring_kernel<P, GROUPS, SPG, GT, HALVES><<<grid, GROUPS * GT, smem, st>>>(
         static_cast<const double*>(labels->ptr), labels->stride[0], static_cast<const double*>(logits->ptr), logits->stride[0],
-        static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], (unsigned)logits->shape[1], row_bytes, flag);
+        static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], (unsigned)logits->shape[1], row_bytes, flag, sce_exp_tab());
     return cudaGetLastError();
 }
 
@@ -207,7 +212,7 @@ template <int K>
 __global__ void __launch_bounds__(512, 1)
 softmax_ce_ring_narrow_kernel(const double* __restrict__ labels, long long l_sr, const double* __restrict__ logits, long long z_sr,
                               double* __restrict__ out, long long o_s, long long rows, unsigned cols, unsigned half_bytes, unsigned copy_bytes,
-                              int spw, int* __restrict__ flag) {
+                              int spw, int* __restrict__ flag, int exp_tab) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) unsigned long long bars[64];
     const int warps = blockDim.x >> 5, w = threadIdx.x >> 5;
@@ -264,8 +269,13 @@ softmax_ce_ring_narrow_kernel(const double* __restrict__ labels, long long l_sr,
         for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
         const double mm = m == -INFINITY ? 0.0 : m;    // (fmax skips NaN, exp_nonpos does not: a NaN logit makes `se` NaN)
         double se = 0.0;
+        if (exp_tab) {
 #pragma unroll
-        for (int e = 0; e < 4 * K; ++e) se += exp_nonpos(z[e] - mm);
+            for (int e = 0; e < 4 * K; ++e) se += exp_nonpos_tab(z[e] - mm);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4 * K; ++e) se += exp_nonpos(z[e] - mm);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             se += __shfl_xor_sync(0xffffffffu, se, off);
@@ -299,7 +309,7 @@ cudaError_t launch_ring_narrow(const adb_tensor* labels, const adb_tensor* logit
     const int smem = warps * spw * 2 * (int)half_bytes;
     softmax_ce_ring_narrow_kernel<K><<<grid, warps * 32, smem, st>>>(
         static_cast<const double*>(labels->ptr), labels->stride[0], static_cast<const double*>(logits->ptr), logits->stride[0],
-        static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], cols, half_bytes, copy_bytes, spw, flag);
+        static_cast<double*>(out->ptr), out->stride[0], logits->shape[0], cols, half_bytes, copy_bytes, spw, flag, sce_exp_tab());
     return cudaGetLastError();
 }
 
