@@ -296,6 +296,31 @@ def _survey(top):
     return uploads, leaf_ids, interior, flops
 
 
+def schedule_pipeline(uploads_of, leaves_of, weight_of, small_bytes):
+    """The order of `eval_many`'s uploads and outputs (pure function of sizes; CPU-tested).
+    uploads_of[i]: (leaf id, bytes) of the host leaves output i still needs uploaded; leaves_of[i]: ids of ALL its leaves;
+    weight_of[i]: contraction flops of the job (connected component) output i belongs to.
+    Upload order: leaves too small to matter first (an output that needs nothing else - the outer-product gradient of
+    'ijkl,jl->ik' needs only the 128 x 128 operand - can start, and its result can start travelling back, at once), then the
+    leaves of the HEAVIEST job (its kernels are the long pole of the pass), then the rest in the order given.
+    Returns (leaf ids in upload order, ready[i] = bytes queued on the upload stream when the last leaf of output i is on
+    the device): outputs are issued by increasing ready[i] - stable - so that on each stream nothing ready waits behind
+    an output whose operand is still on the wire."""
+    heaviest = max(list(weight_of) or [0.0])
+    order_key = {}
+    for i, ups in enumerate(uploads_of):
+        for lid, nbytes in ups:
+            cls = 0 if nbytes < small_bytes else (1 if weight_of[i] >= heaviest else 2)
+            order_key.setdefault(lid, ((cls, len(order_key)), nbytes))
+    upload_order = sorted(order_key, key=lambda lid: order_key[lid][0])
+    position, queued = {}, 0
+    for lid in upload_order:
+        queued += order_key[lid][1]
+        position[lid] = queued
+    ready = [max([position.get(lid, 0) for lid in leaves] or [0]) for leaves in leaves_of]
+    return upload_order, ready
+
+
 def eval_many(tops):
     """`[t() for t in tops]` as ONE pipelined pass: returns the host values (and memoises them in `node.cached`, as
     reference node.py:42-46 does) while host->device copies of the leaves, kernels and device->host copies of the
@@ -354,31 +379,21 @@ def eval_many(tops):
         for x in g:
             plans[id(x)] = plan
             stream_of[id(x)] = light if is_light else main
-    # upload order: leaves too small to matter first (an output that needs nothing else - the outer-product gradient of
-    # 'ijkl,jl->ik' needs only the 128 x 128 operand - can start, and its result can start travelling back, at once), then
-    # the leaves of the HEAVIEST job (its kernels are the long pole of the pass), then the rest in the order given
-    order_key = {}
-    for i, x in enumerate(todo):
-        w = weight[find(i)]
-        for leaf, value in wanted[id(x)]:
-            key = (0 if value.nbytes < PIPELINE_MIN_BYTES else (1 if w >= heaviest else 2), len(order_key))
-            order_key.setdefault(id(leaf), (key, leaf, value))
-    position = {}                    # id(leaf) -> bytes queued on the upload stream up to and including this leaf
-    queued = 0
-    for key, leaf, value in sorted(order_key.values(), key=lambda e: e[0]):
+    uploads_of = [[(id(leaf), value.nbytes) for leaf, value in wanted[id(x)]] for x in todo]
+    leaf_obj = {id(leaf): (leaf, value) for x in todo for leaf, value in wanted[id(x)]}
+    upload_order, ready = schedule_pipeline(uploads_of, [info[id(x)][0] for x in todo], [weight[find(i)] for i in range(len(todo))],
+                                            PIPELINE_MIN_BYTES)
+    for lid in upload_order:
+        leaf, value = leaf_obj[lid]
         if leaf._dev is None:
             leaf._dev, staged = to_device_async(value, h2d)
             keep.append(staged)
             ev = t.cuda.Event(enable_timing=tr is not None)
             ev.record(h2d)
             leaf_event[id(leaf)] = ev
-            queued += value.nbytes
-            position[id(leaf)] = queued
             if tr is not None:
                 tr.append(("uploaded %s %s" % (leaf.name, value.shape), ev))
-    # issue order: an output whose leaves arrive earlier goes first (stable: the caller's order among equals), so that on each
-    # stream nothing ready waits behind an output whose operand is still on the wire
-    ready_at = {id(x): max([position.get(lid, 0) for lid in info[id(x)][0]] or [0]) for x in todo}
+    ready_at = {id(x): ready[i] for i, x in enumerate(todo)}
     rank_of = {id(x): i for i, x in enumerate(pending)}
     pending = sorted(pending, key=lambda x: (ready_at.get(id(x), 0), rank_of[id(x)]))
     # 3. kernels per output on its job's stream; each result's download is queued behind its own kernels only

@@ -275,3 +275,26 @@ def test_c3_parity_verdict_on_measured_records():
     assert not c3_parity_ok(n8, 3e-12, True, 3.58e-9, 3.89e-8, 2.42e-11)                     # gradients at identical inputs off the bar
     assert not c3_parity_ok([2e-12] + n8[1:], 1e-13, True, 3.58e-9, 3.89e-8, 2.42e-11)       # loss at identical weights off the bar
     assert not c3_parity_ok(n8, 1e-13, True, 1e-7, 3.89e-8, 2.42e-11)                        # weights beyond the 1-ulp noise floor
+
+
+def test_eval_many_schedule_uploads_small_first_then_heaviest_job():
+    """core/engine.py: schedule_pipeline - the order of eval_many's uploads and outputs on the einsum sweep of bench.py
+    (C2a 8192^2 GEMMs, C2b batched GEMMs, C2c 'ijkl,jl->ik' whose gradient w.r.t. the big operand needs only the small one)."""
+    from autodiff_b200.core.engine import schedule_pipeline
+    MB = 1 << 20
+    A1, B1, A2, B2, A3, B3 = range(6)                      # leaf ids: C2a A/B (512 MB), C2b A/B (512 MB), C2c A (2 GB) / B (128 KB)
+    size = {A1: 512 * MB, B1: 512 * MB, A2: 512 * MB, B2: 512 * MB, A3: 2048 * MB, B3: 128 * 1024}
+    #            e         dA     dB     e         dA     dB     e         dA     dB
+    leaves = [[A1, B1], [B1], [A1], [A2, B2], [B2], [A2], [A3, B3], [B3], [A3]]
+    weights = [3.3e12] * 3 + [4.1e11] * 3 + [1.6e9] * 3
+    uploads = [[(l, size[l]) for l in ls] for ls in leaves]
+    order, ready = schedule_pipeline(uploads, leaves, weights, 1 * MB)
+    assert order == [B3, A1, B1, A2, B2, A3]               # tiny leaf, the heaviest job's operands, the rest as given
+    assert ready[7] == size[B3]                             # C2c dA: computable as soon as the 128 KB operand is up
+    issue = sorted(range(9), key=lambda i: (ready[i], i))
+    assert issue[0] == 7 and issue[1] == 2 and set(issue[-2:]) == {6, 8}      # then C2a dB (needs only A), ..., C2c e / dB last
+    assert ready[0] == ready[1] == size[B3] + size[A1] + size[B1]
+    # leaves already on the device (not in `uploads`) cost nothing; outputs without host leaves are ready at once
+    order, ready = schedule_pipeline([[], [(A1, size[A1])]], [[B1], [A1, B1]], [1.0, 1.0], MB)
+    assert order == [A1] and ready == [0, size[A1]]
+    assert schedule_pipeline([], [], [], MB) == ([], [])
